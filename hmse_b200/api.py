@@ -1,0 +1,268 @@
+"""Host side of the hot path: chunk(), digest(), dedup(), compress(), similarity() with the
+same names, argument meaning and return layout as the CPU oracle (oracle/__init__.py), served
+by the sm_100a kernels behind the C ABI (include/hmse.h).  Spec layers: L2 chunking
+README.md:289, L3 digest/dedup README.md:290 + 1288-1292, L1 DEFLATE README.md:288,
+L4 MinHash/LSH README.md:291.
+
+Inputs may be host buffers (bytes / numpy) - they are staged to the device and results come back
+as numpy arrays, exactly the oracle's return types - or CUDA torch tensors, in which case
+results stay on the device as torch tensors.  There is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CdcCfg, HmseError
+from .config import CDCConfig, SimConfig
+
+_PAD = 64  # slack after every staged buffer: kernels read whole 16-byte vectors
+
+
+def _cdc_struct(cfg: CDCConfig) -> CdcCfg:
+    s = CdcCfg()
+    s.min_size, s.avg_size, s.max_size, s.reserved = cfg.min_size, cfg.avg_size, cfg.max_size, 0
+    s.mask_s, s.mask_l = cfg.mask_s, cfg.mask_l
+    C.memmove(s.gear, cfg.gear.ctypes.data, 2048)
+    return s
+
+
+class Context:
+    """One hmse_ctx (device scratch + error text) on one CUDA device."""
+
+    def __init__(self, device: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("hmse_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.init()
+        h = C.c_void_p()
+        rc = self.lib.hmse_create(self.device, C.byref(h))
+        if rc != 0:
+            raise HmseError(rc, "hmse_create failed")
+        self.h = h
+        self._cdc_cache = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hmse_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def check(self, rc: int):
+        if rc != 0:
+            raise HmseError(rc, (self.lib.hmse_last_error(self.h) or b"").decode("utf-8", "replace"))
+
+    @property
+    def stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def tdev(self) -> torch.device:
+        return torch.device("cuda", self.device)
+
+    def cdc_struct(self, cfg: CDCConfig) -> CdcCfg:
+        s = self._cdc_cache.get(cfg)
+        if s is None:
+            s = self._cdc_cache[cfg] = _cdc_struct(cfg)
+        return s
+
+    def empty(self, n: int, dtype) -> torch.Tensor:
+        return torch.empty(int(n), dtype=dtype, device=self.tdev)
+
+    def stage(self, data) -> torch.Tensor:
+        """uint8 device tensor with 16-byte-aligned storage and >= _PAD readable bytes after it."""
+        if isinstance(data, torch.Tensor):
+            if data.dtype != torch.uint8 or not data.is_cuda:
+                raise TypeError("device input must be a CUDA uint8 tensor")
+            data = data.contiguous().view(-1)
+            if data.data_ptr() % 16 == 0:
+                return data
+            buf = self.empty(data.numel() + _PAD, torch.uint8)
+            buf[:data.numel()].copy_(data)
+            return buf[:data.numel()]
+        host = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        if host.dtype != np.uint8:
+            raise TypeError("data must be uint8")
+        buf = self.empty(host.size + _PAD, torch.uint8)
+        if host.size:
+            buf[:host.size].copy_(torch.from_numpy(host.reshape(-1).copy() if not host.flags.writeable else host.reshape(-1)))
+        return buf[:host.size]
+
+    def stage_u64(self, x) -> torch.Tensor:
+        """int64 device tensor holding uint64 bit patterns."""
+        if isinstance(x, torch.Tensor):
+            if x.dtype not in (torch.int64, torch.uint64) or not x.is_cuda:
+                raise TypeError("device cuts must be a CUDA int64/uint64 tensor")
+            return x.contiguous().view(torch.int64)
+        a = np.ascontiguousarray(x, dtype=np.uint64).view(np.int64)
+        return torch.from_numpy(a.copy()).to(self.tdev)
+
+    # -- L2 -------------------------------------------------------------------------------
+    def chunk(self, d: torch.Tensor, cfg: CDCConfig) -> torch.Tensor:
+        n = d.numel()
+        cap = n // cfg.min_size + 2
+        cuts = self.empty(cap, torch.int64)
+        nc = C.c_uint64(0)
+        self.check(self.lib.hmse_chunk(self.h, d.data_ptr(), n, C.byref(self.cdc_struct(cfg)), cuts.data_ptr(), cap,
+                                       C.byref(nc), self.stream))
+        return cuts[:nc.value]
+
+    def chunk_scan(self, d: torch.Tensor, cfg: CDCConfig):
+        self.check(self.lib.hmse_chunk_scan(self.h, d.data_ptr(), d.numel(), C.byref(self.cdc_struct(cfg)), self.stream))
+
+    def chunk_resolve(self, d: torch.Tensor, cfg: CDCConfig, n_own: int, eof: bool, entry: int):
+        """Returns (cuts int64 tensor, exit offset).  Requires a prior chunk_scan(d, cfg)."""
+        n = d.numel()
+        own = n if eof else n_own
+        cap = own // cfg.min_size + 2
+        cuts = self.empty(cap, torch.int64)
+        nc, ex = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.hmse_chunk_resolve(self.h, d.data_ptr(), n_own, n, int(eof), entry, cuts.data_ptr(), cap,
+                                               C.byref(nc), C.byref(ex), self.stream))
+        return cuts[:nc.value], ex.value
+
+    # -- L3 -------------------------------------------------------------------------------
+    def digest(self, d: torch.Tensor, cuts: torch.Tensor, start0: int = 0) -> torch.Tensor:
+        m = cuts.numel()
+        out = self.empty(m * 32, torch.uint8)
+        self.check(self.lib.hmse_digest(self.h, d.data_ptr(), start0, cuts.data_ptr(), m, out.data_ptr(), self.stream))
+        return out.view(m, 32)
+
+    def dedup(self, digests: torch.Tensor):
+        m = digests.shape[0]
+        canon = self.empty(m, torch.int64)
+        first = self.empty(m, torch.uint8)
+        self.check(self.lib.hmse_dedup(self.h, digests.data_ptr(), m, canon.data_ptr(), first.data_ptr(), self.stream))
+        return canon, first.view(torch.bool)
+
+    # -- L1 -------------------------------------------------------------------------------
+    def compress(self, d: torch.Tensor, cuts: torch.Tensor, select: Optional[torch.Tensor], zdict: Optional[torch.Tensor],
+                 level: int = 6, start0: int = 0, out_cap: Optional[int] = None):
+        m = cuts.numel() if select is None else select.numel()
+        offsets = self.empty(m + 1, torch.int64)
+        if out_cap is None:
+            # a dynamic block never beats stored by more than the input size: input bytes + per-chunk slack
+            span = int(d.numel())
+            out_cap = span + 64 * m + 1024 if select is None else None
+        if out_cap is None:
+            out_cap = int(d.numel()) + 64 * m + 1024
+        total = C.c_uint64(0)
+        zp = zdict.data_ptr() if zdict is not None and zdict.numel() else None
+        zl = zdict.numel() if zdict is not None else 0
+        sp = select.data_ptr() if select is not None else None
+        for _ in range(2):
+            out = self.empty(out_cap, torch.uint8)
+            rc = self.lib.hmse_compress(self.h, d.data_ptr(), start0, cuts.data_ptr(), sp, m, zp, zl, level,
+                                        out.data_ptr(), out_cap, offsets.data_ptr(), C.byref(total), self.stream)
+            if rc == _lib.HMSE_E_CAPACITY and total.value > out_cap:
+                out_cap = int(total.value)
+                continue
+            self.check(rc)
+            return out[:total.value], offsets
+        raise HmseError(_lib.HMSE_E_CAPACITY, "hmse_compress: capacity retry failed")
+
+    # -- L4 -------------------------------------------------------------------------------
+    def minhash(self, d: torch.Tensor, cuts: torch.Tensor, cfg: SimConfig, start0: int = 0) -> torch.Tensor:
+        m = cuts.numel()
+        seeds = torch.from_numpy(cfg.seed_array.view(np.int32).copy()).to(self.tdev)
+        sig = self.empty(m * cfg.n_perm, torch.int32)
+        self.check(self.lib.hmse_minhash(self.h, d.data_ptr(), start0, cuts.data_ptr(), m, seeds.data_ptr(), cfg.n_perm,
+                                         sig.data_ptr(), self.stream))
+        return sig.view(m, cfg.n_perm)
+
+    def lsh_keys(self, sig: torch.Tensor, cfg: SimConfig) -> torch.Tensor:
+        m = sig.shape[0]
+        keys = self.empty(m * cfg.bands, torch.int64)
+        self.check(self.lib.hmse_lsh_keys(self.h, sig.data_ptr(), m, cfg.bands, cfg.rows, keys.data_ptr(), self.stream))
+        return keys.view(m, cfg.bands)
+
+    def lsh_buckets(self, keys: torch.Tensor, id_base: int = 0):
+        m, b = keys.shape
+        band = self.empty(m * b, torch.int32)
+        key = self.empty(m * b, torch.int64)
+        ids = self.empty(m * b, torch.int64)
+        self.check(self.lib.hmse_lsh_buckets(self.h, keys.data_ptr(), m, b, id_base, band.data_ptr(), key.data_ptr(),
+                                             ids.data_ptr(), self.stream))
+        return band, key, ids
+
+
+_contexts = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    if not torch.cuda.is_available():
+        raise RuntimeError("hmse_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    ctx = _contexts.get(dev)
+    if ctx is None:
+        ctx = _contexts[dev] = Context(dev)
+    return ctx
+
+
+def _is_dev(x) -> bool:
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _np_u64(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint64)
+
+
+# ---- the oracle-shaped API --------------------------------------------------------------------
+
+def chunk(data, cfg: CDCConfig = CDCConfig(), ctx: Optional[Context] = None):
+    """cuts: uint64[n] exclusive end offsets, strictly increasing, cuts[-1] == len(data)."""
+    ctx = ctx or default_context()
+    cuts = ctx.chunk(ctx.stage(data), cfg)
+    return cuts if _is_dev(data) else _np_u64(cuts)
+
+
+def digest(data, cuts, start0: int = 0, ctx: Optional[Context] = None):
+    """uint8[n, 32]: SHA-256 of every raw chunk."""
+    ctx = ctx or default_context()
+    out = ctx.digest(ctx.stage(data), ctx.stage_u64(cuts), start0)
+    return out if _is_dev(data) else out.cpu().numpy()
+
+
+def dedup(digests, ctx: Optional[Context] = None):
+    """(canon int64[n], is_first bool[n]): canon[i] = first index with the same digest."""
+    ctx = ctx or default_context()
+    dev = _is_dev(digests)
+    dg = digests if dev else torch.from_numpy(np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 32)).to(ctx.tdev)
+    canon, first = ctx.dedup(dg.contiguous())
+    return (canon, first) if dev else (canon.cpu().numpy(), first.cpu().numpy())
+
+
+def compress(data, cuts, select, zdict: bytes = b"", level: int = 6, start0: int = 0, ctx: Optional[Context] = None):
+    """(blob uint8[...], offsets uint64[m+1]); slice j is one zlib stream (FDICT when zdict)."""
+    ctx = ctx or default_context()
+    dev = _is_dev(data)
+    d = ctx.stage(data)
+    sel = None if select is None else ctx.stage_u64(select)
+    zd = ctx.stage(zdict) if not isinstance(zdict, torch.Tensor) else zdict
+    blob, offs = ctx.compress(d, ctx.stage_u64(cuts), sel, zd, level, start0)
+    return (blob, offs) if dev else (blob.cpu().numpy(), _np_u64(offs))
+
+
+def similarity(data, cuts, cfg: SimConfig = SimConfig(), start0: int = 0, ctx: Optional[Context] = None):
+    """(sig uint32[n, n_perm], keys uint64[n, bands], (band u32, key u64, id u64) sorted)."""
+    ctx = ctx or default_context()
+    dev = _is_dev(data)
+    d = ctx.stage(data)
+    sig = ctx.minhash(d, ctx.stage_u64(cuts), cfg, start0)
+    keys = ctx.lsh_keys(sig, cfg)
+    band, key, ids = ctx.lsh_buckets(keys)
+    if dev:
+        return sig, keys, (band, key, ids)
+    return (sig.cpu().numpy().view(np.uint32), _np_u64(keys),
+            (band.cpu().numpy().view(np.uint32), _np_u64(key), _np_u64(ids)))

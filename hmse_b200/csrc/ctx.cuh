@@ -1,0 +1,87 @@
+// ctx.cuh - context, scratch slots and error plumbing shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hmse.h"
+
+#define HMSE_API extern "C" __attribute__((visibility("default")))
+
+enum HmseSlot {
+    SLOT_CDC_CFG = 0,   // device copy of gear table + parameters (CdcDev)
+    SLOT_CDC_BITS,      // MaskS / MaskL candidate bitmaps, one bit per byte each
+    SLOT_CDC_SEG,       // per-segment speculative + fix-up cut lists
+    SLOT_CDC_META,      // per-segment entry/exit/count records, flags
+    SLOT_SCAN,          // block sums of the generic exclusive scan
+    SLOT_SHA_MISC,      // work counter
+    SLOT_DEDUP_TABLE,   // open-addressing table of chunk indices
+    SLOT_DEDUP_MISC,    // owner histogram / offsets for the partition step
+    SLOT_DEFLATE_STAGE, // per-chunk worst-case output slots
+    SLOT_DEFLATE_MISC,  // sizes, slot offsets, class lists, counters
+    SLOT_DEFLATE_DICT,  // hash-sorted index of the preset dictionary
+    SLOT_DEFLATE_WORK,  // per-CTA match scratch for the large class
+    SLOT_MINHASH_MISC,  // work counter
+    SLOT_LSH_SORT,      // radix-sort ping-pong buffers
+    SLOT_LSH_MISC,      // digit histograms
+    SLOT_CORPUS,
+    SLOT_COUNT
+};
+
+struct hmse_ctx {
+    int device;
+    char err[512];
+    void* slot[SLOT_COUNT];
+    size_t slot_bytes[SLOT_COUNT];
+    uint64_t* pinned;  // small pinned host mailbox (4 KiB)
+    int sm_count;
+    // CDC state carried from scan to resolve
+    uint64_t cdc_n_avail;
+    hmse_cdc_cfg cdc_cfg;
+    int cdc_cfg_valid;
+    int cdc_have_scan;
+    int cdc_rounds;
+    // resolve state (incremental re-resolve)
+    uint64_t seg_len, n_seg, seg_cap;
+    uint64_t res_n_own;
+    int res_eof, res_valid;
+    // deflate dictionary cache key
+    const void* dict_ptr;
+    uint64_t dict_key;
+    uint32_t dict_len;
+    int dict_valid;
+};
+
+#define HMSE_FAIL(ctx, code, ...)                              \
+    do {                                                       \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+        return (code);                                         \
+    } while (0)
+
+#define HMSE_CUDA(ctx, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e__));                                                 \
+            return HMSE_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define HMSE_LAUNCH_CHECK(ctx) HMSE_CUDA(ctx, cudaGetLastError())
+
+#define HMSE_SCRATCH(ctx, var, type, slot, bytes)                  \
+    type var = (type)hmse_scratch((ctx), (slot), (size_t)(bytes)); \
+    if (!(var)) return HMSE_E_NOMEM
+
+// Grow-only scratch.  Returns nullptr (and sets err) on failure.  A grow synchronises the device
+// (cudaFree) - steady-state calls with stable sizes never reallocate.
+void* hmse_scratch(hmse_ctx* ctx, int slot, size_t bytes);
+
+// Exclusive prefix sum of n u64 values (in may equal out).  d_total (device, may be null)
+// receives the grand total.  Uses SLOT_SCAN.  Asynchronous on `stream`.
+int hmse_exclusive_scan_u64(hmse_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n,
+                            uint64_t* d_total, cudaStream_t stream);
+
+static inline uint64_t div_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

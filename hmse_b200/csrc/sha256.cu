@@ -1,0 +1,146 @@
+// sha256.cu - L3 digest: FIPS 180-4 SHA-256 of every raw chunk (spec: README.md:290, 2518-2561;
+// the skeleton's mbedtls_sha256 call at README.md:2543).  Integer-ALU bound, no tensor cores.
+//
+// One hash is strictly serial, so parallelism is across chunks: every LANE owns one chunk at a
+// time and pulls the next one from a global counter when it finishes (persistent lanes), which
+// keeps warps converged on the 64-round block function while chunk lengths vary 2-32 KiB.
+// Full blocks are read as aligned 32-bit words and byte-permuted into big-endian order with one
+// PRMT each (the chunk start is byte-unaligned); only the last one or two blocks of a chunk take
+// the byte-wise padding path.
+#include "ctx.cuh"
+
+namespace {
+
+__constant__ uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98,
+    0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786,
+    0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8,
+    0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13,
+    0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819,
+    0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a,
+    0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7,
+    0xc67178f2};
+
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
+
+__device__ __forceinline__ void sha256_block(uint32_t (&H)[8], uint32_t (&W)[16]) {
+    uint32_t a = H[0], b = H[1], c = H[2], d = H[3], e = H[4], f = H[5], g = H[6], h = H[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = W[(i + 1) & 15], w2 = W[(i + 14) & 15];
+            uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            W[i & 15] = W[i & 15] + s0 + W[(i + 9) & 15] + s1;
+        }
+        uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = h + S1 + ch + K256[i] + W[i & 15];
+        uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        h = g;
+        g = f;
+        f = e;
+        e = d + t1;
+        d = c;
+        c = b;
+        b = a;
+        a = t1 + t2;
+    }
+    H[0] += a; H[1] += b; H[2] += c; H[3] += d; H[4] += e; H[5] += f; H[6] += g; H[7] += h;
+}
+
+constexpr int SHA_THREADS = 128;
+
+__global__ void __launch_bounds__(SHA_THREADS)
+sha256_kernel(const uint8_t* __restrict__ data, uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t n_chunks,
+              uint8_t* __restrict__ digests, unsigned long long* __restrict__ counter) {
+    uint32_t H[8], W[16];
+    uint64_t j = 0, s = 0, len = 0, blk = 0, nblk = 0;
+    bool have = false, done = false;
+    for (;;) {
+        if (!have && !done) {
+            j = atomicAdd(counter, 1ull);
+            if (j >= n_chunks) {
+                done = true;
+            } else {
+                s = j ? cuts[j - 1] : start0;
+                len = cuts[j] - s;
+                nblk = (len + 9 + 63) >> 6;
+                blk = 0;
+                H[0] = 0x6a09e667; H[1] = 0xbb67ae85; H[2] = 0x3c6ef372; H[3] = 0xa54ff53a;
+                H[4] = 0x510e527f; H[5] = 0x9b05688c; H[6] = 0x1f83d9ab; H[7] = 0x5be0cd19;
+                have = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (have) {
+            const uint64_t off = blk << 6;
+            if (off + 68 <= len) {
+                // full block with >= 4 bytes of the same chunk after it: aligned words + PRMT
+                const uint8_t* p = data + s + off;
+                const unsigned k = (unsigned)((uintptr_t)p & 3);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(p - k);
+                const uint32_t sel = 0x0123u + 0x1111u * k;
+                uint32_t lo = __ldg(wp);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    uint32_t hi = __ldg(wp + i + 1);
+                    W[i] = __byte_perm(lo, hi, sel);
+                    lo = hi;
+                }
+            } else {
+                // tail: message bytes, 0x80, zeros, 64-bit big-endian bit length in the last block
+                const uint8_t* p = data + s;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        uint64_t o = off + 4 * i + b;
+                        uint32_t v = o < len ? (uint32_t)p[o] : (o == len ? 0x80u : 0u);
+                        w = (w << 8) | v;
+                    }
+                    W[i] = w;
+                }
+                if (blk == nblk - 1) {
+                    const uint64_t bits = len << 3;
+                    W[14] = (uint32_t)(bits >> 32);
+                    W[15] = (uint32_t)bits;
+                }
+            }
+            sha256_block(H, W);
+            blk++;
+            if (blk == nblk) {
+                uint4* o = reinterpret_cast<uint4*>(digests + (j << 5));
+                o[0] = make_uint4(__byte_perm(H[0], 0, 0x0123), __byte_perm(H[1], 0, 0x0123),
+                                  __byte_perm(H[2], 0, 0x0123), __byte_perm(H[3], 0, 0x0123));
+                o[1] = make_uint4(__byte_perm(H[4], 0, 0x0123), __byte_perm(H[5], 0, 0x0123),
+                                  __byte_perm(H[6], 0, 0x0123), __byte_perm(H[7], 0, 0x0123));
+                have = false;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+HMSE_API int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
+                           uint64_t n_chunks, uint8_t* d_digests, void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_chunks == 0) return HMSE_OK;
+    if (!d_data || !d_cuts || !d_digests) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_digest: null pointer");
+    if ((uintptr_t)d_digests & 15) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_digests must be 16-byte aligned");
+    if ((uintptr_t)d_data & 3) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_data must be 4-byte aligned");
+    HMSE_SCRATCH(ctx, counter, unsigned long long*, SLOT_SHA_MISC, 64);
+    HMSE_CUDA(ctx, cudaMemsetAsync(counter, 0, 8, st));
+    // persistent lanes: enough warps to fill the machine, never more lanes than chunks
+    uint64_t blocks = div_up64(n_chunks, SHA_THREADS);
+    const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    sha256_kernel<<<(unsigned)blocks, SHA_THREADS, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_digests, counter);
+    HMSE_LAUNCH_CHECK(ctx);
+    return HMSE_OK;
+}

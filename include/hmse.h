@@ -1,0 +1,161 @@
+/* hmse.h - C ABI of libhmse_b200.so: the HMSE data-reduction hot path on B200 (sm_100a).
+ *
+ * The reference (1Jamie/HMSE) defines this path only as a spec plus ESP-IDF skeletons; it has
+ * no FFI.  Each entry point below replaces the spec function cited beside it, so a firmware or
+ * host-side maintainer binds these where the skeleton called miniz / mbedtls / murmur3 (see
+ * INTEGRATION.md for the ctypes binding that hmse_b200/ uses and the C call sequence).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  Pointers named d_* are DEVICE pointers owned by the
+ *    caller; everything else is host memory.  `stream` is a cudaStream_t passed as void*.
+ *  - Every call returns an int status (HMSE_OK == 0, negative on error) and never throws;
+ *    hmse_last_error(ctx) returns the text of the last failure on that context.
+ *  - The library owns only scratch inside hmse_ctx (grown on demand, freed by hmse_destroy).
+ *  - Kernels are enqueued on `stream`.  Calls that return a count to the host
+ *    (hmse_chunk*, hmse_compress, hmse_dedup_partition) synchronise `stream` before returning;
+ *    all others are asynchronous and their outputs are valid after the caller syncs `stream`.
+ *  - One ctx per device per thread; a ctx is not thread-safe.
+ *  - There is no CPU fallback: without a CUDA device every call fails with HMSE_E_CUDA.
+ *
+ * Chunk lists: a chunk list is (start0, cuts[n]) - chunk j is [j ? cuts[j-1] : start0, cuts[j]),
+ * offsets relative to d_data.  This is the layout hmse_chunk* writes.
+ */
+#ifndef HMSE_H
+#define HMSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMSE_OK 0
+#define HMSE_E_INVAL (-1)    /* bad argument                                   */
+#define HMSE_E_CAPACITY (-2) /* an output buffer is too small; needed size is returned */
+#define HMSE_E_CUDA (-3)     /* CUDA runtime error (text in hmse_last_error)   */
+#define HMSE_E_NOMEM (-4)    /* scratch allocation failed                      */
+
+#define HMSE_ABI_VERSION 1
+
+typedef struct hmse_ctx hmse_ctx;
+
+/* FastCDC parameters (spec: README.md:289, 2444-2446; masks and Gear table per the FastCDC
+ * paper the spec cites at README.md:2753-2755).  64 <= min <= avg <= max <= 1 MiB. */
+typedef struct hmse_cdc_cfg {
+    uint32_t min_size;
+    uint32_t avg_size;
+    uint32_t max_size;
+    uint32_t reserved;
+    uint64_t mask_s; /* tested while chunk length <  avg_size */
+    uint64_t mask_l; /* tested while chunk length >= avg_size */
+    uint64_t gear[256];
+} hmse_cdc_cfg;
+
+int hmse_abi_version(void);
+int hmse_create(int device, hmse_ctx** out);
+void hmse_destroy(hmse_ctx* ctx);
+const char* hmse_last_error(hmse_ctx* ctx);
+/* Bytes of device scratch currently held by ctx. */
+uint64_t hmse_scratch_bytes(hmse_ctx* ctx);
+
+/* ---- L2 chunking: replaces rabin_slide + the boundary loop of benchmark_fastcdc
+ *      (README.md:2456-2464, 2475-2490). ------------------------------------------------- */
+
+/* Whole stream: cuts of d_data[0:n).  d_cuts receives *n_cuts exclusive end offsets, strictly
+ * increasing, last == n.  d_data must be 16-byte aligned.  On HMSE_E_CAPACITY *n_cuts holds the
+ * required capacity. */
+int hmse_chunk(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n, const hmse_cdc_cfg* cfg,
+               uint64_t* d_cuts, uint64_t cap, uint64_t* n_cuts, void* stream);
+
+/* Sharded stream, step 1: candidate scan of d_data[0:n_avail) into ctx scratch. */
+int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_avail, const hmse_cdc_cfg* cfg,
+                    void* stream);
+/* Sharded stream, step 2 (repeatable): the chain of chunk starts s, entry <= s < n_own, over the
+ * last scanned buffer.  eof != 0: the buffer ends the stream (n_own is ignored, = n_avail).
+ * eof == 0: the stream continues; n_avail >= n_own + max_size is required.  *exit_off receives
+ * the last cut (first chunk start >= n_own): the next shard's entry is exit_off - n_own.
+ * Calling it again with another `entry` re-resolves incrementally. */
+int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_own, uint64_t n_avail, int eof,
+                       uint64_t entry, uint64_t* d_cuts, uint64_t cap, uint64_t* n_cuts,
+                       uint64_t* exit_off, void* stream);
+/* Number of speculative fix-up rounds the last resolve needed (diagnostic). */
+int hmse_chunk_last_rounds(hmse_ctx* ctx);
+
+/* ---- L3 digest + exact dedup: replaces mbedtls_sha256 (README.md:2543) and the ChunkIndex
+ *      lookup/insert rule (README.md:1264-1269, 1288-1292). -------------------------------- */
+
+/* d_digests[j][32] = SHA-256 of chunk j. */
+int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
+                uint64_t n_chunks, uint8_t* d_digests, void* stream);
+
+/* d_canon[i] = smallest j with digest j == digest i; d_is_first[i] = (canon == i). */
+int hmse_dedup(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, int64_t* d_canon,
+               uint8_t* d_is_first, void* stream);
+
+/* Multi-GPU dedup, sender side: groups records {digest[32], gid u64} by owner = le32(digest) %
+ * world into d_records (40 B each, owner-major), d_perm[k] = local index of record k,
+ * counts[world] (host) = records per owner.  gid = id_base + local index. */
+int hmse_dedup_partition(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, uint64_t id_base,
+                         uint32_t world, uint8_t* d_records, uint32_t* d_perm, uint64_t* counts,
+                         void* stream);
+/* Owner side: d_canon_gid[k] = smallest gid among records with the same digest as record k. */
+int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_t m, uint64_t* d_canon_gid,
+                       void* stream);
+/* Sender side, after the return exchange: d_canon[d_perm[k]] = d_reply[k];
+ * d_is_first[i] = (canon[i] == id_base + i). */
+int hmse_dedup_scatter(hmse_ctx* ctx, const uint64_t* d_reply, const uint32_t* d_perm, uint64_t n,
+                       uint64_t id_base, int64_t* d_canon, uint8_t* d_is_first, void* stream);
+
+/* ---- L1 DEFLATE: replaces mz_deflateInit2 / mz_deflate(FINISH) (README.md:2374, 2378). --- */
+
+/* Worst-case bytes of one zlib stream for a chunk of `len` bytes. */
+uint64_t hmse_compress_bound(uint64_t len);
+
+/* One RFC 1950 stream (FDICT set when dict_len > 0) per selected chunk, packed back to back in
+ * d_out in selection order; d_offsets[m+1] are the stream boundaries.  d_select[k] is a chunk
+ * index (NULL = chunks 0..m-1).  dict_len <= 32768.  level is accepted for API parity; 1..9 all
+ * run the same match search (tuned against zlib level 6).  *total (host) = d_offsets[m].
+ * On HMSE_E_CAPACITY *total holds the required out_cap. */
+int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
+                  const uint64_t* d_select, uint64_t m, const uint8_t* d_zdict, uint32_t dict_len,
+                  int level, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total,
+                  void* stream);
+
+/* ---- L4 similarity: replaces minhash_compute (README.md:2578-2597) and LSH banding
+ *      (README.md:2231-2235). -------------------------------------------------------------- */
+
+/* d_sig[j][n_perm]: running minimum (from 0xFFFFFFFF) of MurmurHash3_x86_32(4-byte shingle,
+ * d_seeds[p]) over every byte offset of chunk j.  n_perm must be a multiple of 32, <= 256. */
+int hmse_minhash(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
+                 uint64_t n_chunks, const uint32_t* d_seeds, uint32_t n_perm, uint32_t* d_sig,
+                 void* stream);
+/* d_keys[j][bands] = FNV-1a-64 of the band's rows*4 little-endian signature bytes. */
+int hmse_lsh_keys(hmse_ctx* ctx, const uint32_t* d_sig, uint64_t n, uint32_t bands, uint32_t rows,
+                  uint64_t* d_keys, void* stream);
+/* All n*bands triples (band, key, id_base + j) sorted by (band, key, id). */
+int hmse_lsh_buckets(hmse_ctx* ctx, const uint64_t* d_keys, uint64_t n, uint32_t bands,
+                     uint64_t id_base, uint32_t* d_band, uint64_t* d_key, uint64_t* d_id, void* stream);
+
+/* ---- Synthetic corpus (bench/test input, not part of the reference path): renders bytes
+ *      [byte_off, byte_off + n) of the procedural wiki stream defined in oracle/corpus.py. ---- */
+typedef struct hmse_corpus_cfg {
+    uint32_t seed;
+    uint32_t dup_thr;
+    uint32_t near_thr;
+    uint32_t n_lex; /* lexicon entries */
+} hmse_corpus_cfg;
+/* d_art_len[n_articles] (u32) = byte length of each article first_article.. */
+int hmse_corpus_lengths(hmse_ctx* ctx, const hmse_corpus_cfg* cfg, const uint32_t* d_lex_off,
+                        uint64_t first_article, uint64_t n_articles, uint32_t* d_art_len, void* stream);
+/* d_art_off[n_articles+1] = exclusive prefix sum of lengths (stream offset of each article).
+ * Writes stream bytes [byte_off, byte_off+n) to d_out. */
+int hmse_corpus_render(hmse_ctx* ctx, const hmse_corpus_cfg* cfg, const uint8_t* d_lex_blob,
+                       const uint32_t* d_lex_off, uint64_t first_article, uint64_t n_articles,
+                       const uint64_t* d_art_off, uint64_t byte_off, uint64_t n, uint8_t* d_out,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMSE_H */

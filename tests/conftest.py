@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import hmse_b200
+    return hmse_b200.default_context(0)
+
+
+@pytest.fixture(scope="session")
+def corpus8():
+    """8 MiB of the seed-42 procedural wiki corpus (oracle twin generator)."""
+    from oracle import corpus
+    return corpus.generate(8 << 20)
