@@ -41,6 +41,7 @@ SIGNATURES = {
     "hmse_chunk": (_I, [_P, _P, _U64, C.POINTER(CdcCfg), _P, _U64, _PU64, _P]),
     "hmse_chunk_scan": (_I, [_P, _P, _U64, C.POINTER(CdcCfg), _P]),
     "hmse_chunk_resolve": (_I, [_P, _P, _U64, _U64, _I, _U64, _P, _U64, _PU64, _PU64, _P]),
+    "hmse_chunk_candidates": (_I, [_P, _P, _P, _U64, _P]),
     "hmse_chunk_last_rounds": (_I, [_P]),
     "hmse_digest": (_I, [_P, _P, _U64, _P, _U64, _P, _P]),
     "hmse_dedup": (_I, [_P, _P, _U64, _P, _P, _P]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "hmse_dedup_scatter": (_I, [_P, _P, _P, _U64, _U64, _P, _P, _P]),
     "hmse_compress_bound": (_U64, [_U64]),
     "hmse_compress": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _U32, _I, _P, _U64, _P, _PU64, _P]),
+    "hmse_debug_deflate_prof": (_I, [_PU64, _I]),
     "hmse_minhash": (_I, [_P, _P, _U64, _P, _U64, _P, _U32, _P, _P]),
     "hmse_lsh_keys": (_I, [_P, _P, _U64, _U32, _U32, _P, _P]),
     "hmse_lsh_buckets": (_I, [_P, _P, _U64, _U32, _U64, _P, _P, _P, _P]),

@@ -26,7 +26,8 @@ def _cdc_struct(cfg: CDCConfig) -> CdcCfg:
     s = CdcCfg()
     s.min_size, s.avg_size, s.max_size, s.reserved = cfg.min_size, cfg.avg_size, cfg.max_size, 0
     s.mask_s, s.mask_l = cfg.mask_s, cfg.mask_l
-    C.memmove(s.gear, cfg.gear.ctypes.data, 2048)
+    gear = np.ascontiguousarray(cfg.gear, dtype=np.uint64)  # keep the array alive across the copy
+    C.memmove(s.gear, gear.ctypes.data, 2048)
     return s
 
 
@@ -120,6 +121,13 @@ class Context:
 
     def chunk_scan(self, d: torch.Tensor, cfg: CDCConfig):
         self.check(self.lib.hmse_chunk_scan(self.h, d.data_ptr(), d.numel(), C.byref(self.cdc_struct(cfg)), self.stream))
+
+    def chunk_candidates(self, n: int):
+        """(bits_s, bits_l) int64 tensors: candidate bitmaps of the last chunk_scan over n bytes."""
+        words = (n + 63) // 64
+        bs, bl = self.empty(words, torch.int64), self.empty(words, torch.int64)
+        self.check(self.lib.hmse_chunk_candidates(self.h, bs.data_ptr(), bl.data_ptr(), words, self.stream))
+        return bs, bl
 
     def chunk_resolve(self, d: torch.Tensor, cfg: CDCConfig, n_own: int, eof: bool, entry: int):
         """Returns (cuts int64 tensor, exit offset).  Requires a prior chunk_scan(d, cfg)."""

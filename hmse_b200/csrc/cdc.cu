@@ -545,6 +545,19 @@ HMSE_API int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n
     return HMSE_OK;
 }
 
+HMSE_API int hmse_chunk_candidates(hmse_ctx* ctx, uint64_t* d_bits_s, uint64_t* d_bits_l, uint64_t n_words,
+                                   void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    if (!ctx->cdc_have_scan) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_chunk_candidates: no scan");
+    const uint64_t n_tiles = div_up64(ctx->cdc_n_avail, K1_TILE);
+    const uint64_t words = (n_tiles ? n_tiles : 1) * (K1_TILE / 64);
+    if (n_words > words) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_chunk_candidates: n_words exceeds the scanned range");
+    const uint64_t* bits = (const uint64_t*)ctx->slot[SLOT_CDC_BITS];
+    HMSE_CUDA(ctx, cudaMemcpyAsync(d_bits_s, bits, n_words * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    HMSE_CUDA(ctx, cudaMemcpyAsync(d_bits_l, bits + words, n_words * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HMSE_OK;
+}
+
 HMSE_API int hmse_chunk_last_rounds(hmse_ctx* ctx) { return ctx ? (ctx->cdc_rounds >> 1) : 0; }
 
 HMSE_API int hmse_chunk(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n, const hmse_cdc_cfg* cfg, uint64_t* d_cuts,

@@ -1,4 +1,6 @@
 // ctx.cu - context lifetime and scratch management for libhmse_b200.so.
+#include <stdlib.h>
+
 #include <new>
 
 #include "ctx.cuh"
@@ -35,6 +37,7 @@ HMSE_API void hmse_destroy(hmse_ctx* ctx) {
     for (int i = 0; i < SLOT_COUNT; i++)
         if (ctx->slot[i]) cudaFree(ctx->slot[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    free(ctx->dict_host);
     delete ctx;
 }
 

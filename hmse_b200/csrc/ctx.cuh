@@ -46,11 +46,7 @@ struct hmse_ctx {
     uint64_t seg_len, n_seg, seg_cap;
     uint64_t res_n_own;
     int res_eof, res_valid;
-    // deflate dictionary cache key
-    const void* dict_ptr;
-    uint64_t dict_key;
-    uint32_t dict_len;
-    int dict_valid;
+    void* dict_host;  // host copy + checksum of the indexed preset dictionary (deflate.cu)
 };
 
 #define HMSE_FAIL(ctx, code, ...)                              \

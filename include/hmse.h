@@ -79,6 +79,9 @@ int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_avail, cons
 int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_own, uint64_t n_avail, int eof,
                        uint64_t entry, uint64_t* d_cuts, uint64_t cap, uint64_t* n_cuts,
                        uint64_t* exit_off, void* stream);
+/* Copies the first n_words 64-bit words of the MaskS / MaskL candidate bitmaps of the last scan
+ * (bit i of word w = byte position 64*w+i clears the mask on the full 64-byte window). */
+int hmse_chunk_candidates(hmse_ctx* ctx, uint64_t* d_bits_s, uint64_t* d_bits_l, uint64_t n_words, void* stream);
 /* Number of speculative fix-up rounds the last resolve needed (diagnostic). */
 int hmse_chunk_last_rounds(hmse_ctx* ctx);
 
@@ -121,6 +124,10 @@ int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const u
                   const uint64_t* d_select, uint64_t m, const uint8_t* d_zdict, uint32_t dict_len,
                   int level, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total,
                   void* stream);
+
+/* Diagnostic: cycles spent per encoder phase (thread 0 of each CTA, summed over chunks) since
+ * the last reset; out16[15] = chunks encoded.  Host pointer. */
+int hmse_debug_deflate_prof(uint64_t* out16, int reset);
 
 /* ---- L4 similarity: replaces minhash_compute (README.md:2578-2597) and LSH banding
  *      (README.md:2231-2235). -------------------------------------------------------------- */

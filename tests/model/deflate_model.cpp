@@ -1,0 +1,172 @@
+// deflate_model.cpp - sequential CPU model of the GPU DEFLATE encoder (hmse_b200/csrc/deflate.cu).
+// TEST INFRASTRUCTURE: compiled with g++ by tests/model/build.py; shares deflate_core.h with the
+// kernel so the Huffman / header / symbol-map logic is validated against stock zlib on the CPU.
+// Never loaded by the product package.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../hmse_b200/csrc/deflate_core.h"
+
+using namespace dfl;
+
+struct Params {
+    int hash_bytes;   // 3 or 4
+    int chain_own;    // max own-chunk candidates examined
+    int chain_dict;   // max dictionary candidates examined
+    int lazy;         // 0 greedy, 1 zlib-style lazy
+    int too_far;      // drop length-3 matches farther than this (0 = keep)
+};
+
+static inline uint32_t rd(const uint8_t* p, int nb) {
+    uint32_t v = p[0] | (p[1] << 8) | (p[2] << 16);
+    if (nb == 4) v |= (uint32_t)p[3] << 24;
+    return v;
+}
+
+static uint32_t adler32(const uint8_t* d, uint64_t n) {
+    uint32_t a = 1, b = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        a = (a + d[i]) % 65521;
+        b = (b + a) % 65521;
+    }
+    return (b << 16) | a;
+}
+
+extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t* dict, uint32_t dict_len,
+                                  const Params* pr, uint8_t* out, uint64_t cap, uint32_t* stats) {
+    const int HB = pr->hash_bytes;
+    std::vector<std::vector<uint32_t>> own(NBUCKET), dic(NBUCKET);
+    for (uint32_t j = 0; j + HB <= dict_len; j++) dic[hash4(rd(dict + j, HB))].push_back(j);
+    std::vector<uint16_t> mlen(n + 1, 0), mdist(n + 1, 0);
+    for (uint32_t p = 0; p < n; p++) {
+        uint32_t best = 0, bdist = 0;
+        if (p + HB <= n) {
+            const uint32_t maxl = n - p < MAX_MATCH ? n - p : MAX_MATCH;
+            const uint32_t h = hash4(rd(data + p, HB));
+            auto& ob = own[h];
+            int ex = 0;
+            for (int i = (int)ob.size() - 1; i >= 0 && ex < pr->chain_own; i--, ex++) {
+                uint32_t q = ob[i], l = 0;
+                if (p - q > WSIZE) break;
+                while (l < maxl && data[q + l] == data[p + l]) l++;
+                if (l > best) { best = l; bdist = p - q; }
+                if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
+            }
+            auto& db = dic[h];
+            ex = 0;
+            if (best < (uint32_t)NICE_LENGTH && best < maxl)
+                for (int i = (int)db.size() - 1; i >= 0 && ex < pr->chain_dict; i--, ex++) {
+                    uint32_t j = db[i], l = 0;
+                    uint32_t dist = p + dict_len - j;
+                    if (dist > WSIZE) break;
+                    uint32_t lim = dict_len - j < maxl ? dict_len - j : maxl;  // matches do not cross into the chunk
+                    while (l < lim && dict[j + l] == data[p + l]) l++;
+                    if (l > best) { best = l; bdist = dist; }
+                    if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
+                }
+            ob.push_back(p);
+        }
+        if (best < (uint32_t)MIN_MATCH) best = 0;
+        if (best == 3 && pr->too_far && bdist > (uint32_t)pr->too_far) best = 0;
+        mlen[p] = (uint16_t)best;
+        mdist[p] = (uint16_t)(bdist - (best ? 1 : 0));  // stored as dist-1 so 32768 fits
+    }
+    // parse
+    std::vector<uint32_t> tok;  // literal: byte ; match: 1<<31 | len<<16 | (dist-1)
+    uint32_t lit_freq[288] = {0}, dist_freq[32] = {0};
+    uint32_t p = 0, n_match = 0;
+    while (p < n) {
+        uint32_t L = mlen[p];
+        bool lit = L < 3;
+        if (!lit && pr->lazy && L < (uint32_t)MAX_LAZY && p + 1 < n && mlen[p + 1] > L) lit = true;
+        if (lit) {
+            tok.push_back(data[p]);
+            lit_freq[data[p]]++;
+            p++;
+        } else {
+            tok.push_back(0x80000000u | (L << 16) | mdist[p]);
+            uint32_t s, eb, ev;
+            len_sym(L, s, eb, ev);
+            lit_freq[s]++;
+            dist_sym((uint32_t)mdist[p] + 1, s, eb, ev);
+            dist_freq[s]++;
+            p += L;
+            n_match++;
+        }
+    }
+    lit_freq[EOB]++;
+    // cost of the three block types
+    DynHeader h;
+    HuffWork hw;
+    uint32_t lf[288], df[32];
+    memcpy(lf, lit_freq, sizeof lf);
+    memcpy(df, dist_freq, sizeof df);
+    uint64_t dyn_bits = plan_dynamic_header(lf, df, h, hw);
+    uint64_t fix_bits = 3;
+    for (int s = 0; s < NLIT; s++) {
+        dyn_bits += (uint64_t)lit_freq[s] * (h.lit_lens[s] + (s > 256 ? lsym_extra(s) : 0));
+        fix_bits += (uint64_t)lit_freq[s] * (fixed_lit_len(s) + (s > 256 ? lsym_extra(s) : 0));
+    }
+    for (int s = 0; s < NDIST; s++) {
+        dyn_bits += (uint64_t)dist_freq[s] * (h.dist_lens[s] + dsym_extra(s));
+        fix_bits += (uint64_t)dist_freq[s] * (5 + dsym_extra(s));
+    }
+    const uint64_t stored_bytes = (uint64_t)n + 5;  // n <= 65535 in the model
+    const uint64_t hdr = 2 + (dict_len ? 4 : 0);
+    uint64_t best_bits = dyn_bits < fix_bits ? dyn_bits : fix_bits;
+    uint64_t body = (best_bits + 7) / 8;
+    int mode = dyn_bits < fix_bits ? 2 : 1;
+    if (stored_bytes <= body) { mode = 0; body = stored_bytes; }
+    uint64_t total = hdr + body + 4;
+    if (stats) { stats[0] = (uint32_t)tok.size(); stats[1] = n_match; stats[2] = (uint32_t)mode; stats[3] = h.bits; }
+    if (total > cap) return -(int64_t)total;
+    memset(out, 0, total);
+    zlib_header(dict_len != 0, out[0], out[1]);
+    if (dict_len) {
+        uint32_t a = adler32(dict, dict_len);
+        out[2] = a >> 24; out[3] = a >> 16; out[4] = a >> 8; out[5] = a;
+    }
+    if (mode == 0) {
+        uint8_t* o = out + hdr;
+        o[0] = 1;
+        o[1] = n & 0xff; o[2] = n >> 8; o[3] = ~n & 0xff; o[4] = (~n >> 8) & 0xff;
+        memcpy(o + 5, data, n);
+    } else {
+        BitWriter bw{out + hdr, 0};
+        uint32_t lc[288], dc[32];
+        if (mode == 2) {
+            write_dynamic_header(h, bw, 1);
+            assign_codes(h.lit_lens, NLIT, lc);
+            assign_codes(h.dist_lens, NDIST, dc);
+        } else {
+            bw.put(1, 1);
+            bw.put(1, 2);
+            uint8_t fl[288], fd[32];
+            for (int s = 0; s < 288; s++) fl[s] = (uint8_t)fixed_lit_len(s);
+            for (int s = 0; s < 32; s++) fd[s] = 5;
+            assign_codes(fl, 288, lc);
+            assign_codes(fd, 30, dc);
+        }
+        for (uint32_t t : tok) {
+            if (!(t >> 31)) {
+                bw.put(lc[t] & 0xffff, lc[t] >> 16);
+            } else {
+                uint32_t L = (t >> 16) & 0x7fff, D = (t & 0xffff) + 1, s, eb, ev;
+                len_sym(L, s, eb, ev);
+                bw.put(lc[s] & 0xffff, lc[s] >> 16);
+                bw.put(ev, eb);
+                dist_sym(D, s, eb, ev);
+                bw.put(dc[s] & 0xffff, dc[s] >> 16);
+                bw.put(ev, eb);
+            }
+        }
+        bw.put(lc[EOB] & 0xffff, lc[EOB] >> 16);
+        if ((bw.bitpos + 7) / 8 != body) return -1000000 - (int64_t)bw.bitpos;
+    }
+    uint32_t a = adler32(data, n);
+    uint8_t* t = out + hdr + body;
+    t[0] = a >> 24; t[1] = a >> 16; t[2] = a >> 8; t[3] = a;
+    return (int64_t)total;
+}

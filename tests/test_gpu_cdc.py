@@ -128,3 +128,24 @@ def test_virtual_shards_equal_single_stream(ctx, corpus8, world):
     got = np.concatenate(got)
     assert np.array_equal(got, want)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kind", ["text", "random"])
+def test_scan_candidate_bitmaps(ctx, corpus8, kind):
+    """K1 alone: the MaskS / MaskL bitmaps equal the oracle's full-window candidates."""
+    import hmse_b200
+    from oracle.cdc import candidates
+    d = corpus8[:3 << 20] if kind == "text" else corpus.random_bytes(3 << 20)
+    d = np.ascontiguousarray(d[:d.size - 777])       # ragged tail
+    ocfg = OCfg()
+    ctx.chunk_scan(ctx.stage(d), _pcfg(ocfg))
+    bs, bl = ctx.chunk_candidates(d.size)
+    cs, cl = candidates(d, ocfg)
+    for name, bits, want in (("S", bs, cs), ("L", bl, cl)):
+        got = np.flatnonzero(np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little"))
+        got, want = got[got >= 64], want[want >= 64]
+        if not np.array_equal(got, want):
+            miss = np.setdiff1d(want, got)[:8]
+            extra = np.setdiff1d(got, want)[:8]
+            raise AssertionError("%s bitmap (%s): got %d want %d missing %s extra %s" % (name, kind, got.size, want.size,
+                                                                                         miss, extra))

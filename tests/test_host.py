@@ -1,0 +1,73 @@
+"""CPU tests of the host layer: config parity with the oracle, the C-ABI struct marshalling, and
+that the shared library loads and exports every symbol include/hmse.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import hmse_b200
+from hmse_b200 import _lib, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_matches_oracle():
+    assert np.array_equal(hmse_b200.gear_table(), oracle.gear_table())
+    for avg, nc in [(4096, 2), (8192, 2), (8192, 1), (16384, 3), (65536, 2)]:
+        a, b = hmse_b200.CDCConfig.for_avg(avg, nc), oracle.CDCConfig.for_avg(avg, nc)
+        assert (a.min_size, a.avg_size, a.max_size, a.mask_s, a.mask_l, a.gear_seed) == \
+               (b.min_size, b.avg_size, b.max_size, b.mask_s, b.mask_l, b.gear_seed)
+    assert hmse_b200.SimConfig().seeds == oracle.SimConfig().seeds
+    assert hmse_b200.SimConfig().bands == 32 and hmse_b200.SimConfig().rows == 4
+
+
+def test_cdc_struct_marshalling():
+    for _ in range(50):  # the gear array must survive until it is copied (regression: dangling temporary)
+        s = api._cdc_struct(hmse_b200.CDCConfig())
+        assert np.array_equal(np.frombuffer(bytes(s.gear), dtype=np.uint64), oracle.gear_table())
+    assert (s.min_size, s.avg_size, s.max_size) == (2048, 8192, 32768)
+    assert s.mask_s == oracle.PAPER_MASK_S and s.mask_l == oracle.PAPER_MASK_L
+    assert C.sizeof(_lib.CdcCfg) == 16 + 16 + 2048
+
+
+def test_config_validation():
+    with pytest.raises(ValueError):
+        hmse_b200.CDCConfig(32, 64, 128)
+    with pytest.raises(ValueError):
+        hmse_b200.CDCConfig(2048, 1024, 4096)
+    with pytest.raises(ValueError):
+        hmse_b200.SimConfig(128, 16, 4)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hmse.h")).read()
+    declared = set(re.findall(r"\b(hmse_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"hmse_ctx", "hmse_cdc_cfg", "hmse_corpus_cfg"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hmse_abi_version() == _lib.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        hmse_b200.chunk(b"x" * 100)
+    with pytest.raises(RuntimeError):
+        hmse_b200.Context()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hmse_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "tests/model" not in src or f == "deflate_core.h", f
