@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py - ingest GB/s of the HMSE data-reduction hot path (CDC + SHA-256 + dedup + DEFLATE).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle on the host cores
+
+One step = one pass of the hot path over one batch of synthetic templated-wiki text (seed 42,
+generated on the device): at N = 1 BASELINE.json configs[1] (10 GB on one B200); at N > 1 every
+rank owns a 10 GB byte-range shard of ONE N x 10 GB stream (boundary resync + global dedup over an
+NCCL all-to-all), i.e. weak scaling.  Prints ONE JSON line (rank 0).  GB = 1e9 bytes.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ingest GB/s (CDC+SHA-256+dedup+DEFLATE)"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gb", type=float, default=10.0, help="bytes per GPU per step, in GB (1e9)")
+    ap.add_argument("--cpu-sample-mib", type=int, default=128)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle legs (the only places that import oracle/)
+# ------------------------------------------------------------------------------------------------
+def _oracle_pass(data, zd):
+    import numpy as np
+    import oracle
+    cuts = oracle.chunk(data)
+    dg = oracle.digest(data, cuts)
+    canon, first = oracle.dedup(dg)
+    blob, offs = oracle.compress(data, cuts, np.flatnonzero(first), zd)
+    return cuts.size, int(first.sum()), blob.size
+
+
+def cpu_baseline(sample_mib: int):
+    """One process, the Python/NumPy + hashlib + zlib oracle on a bounded sample of the workload."""
+    from oracle import corpus
+    data = corpus.generate(sample_mib << 20)
+    zd = corpus.zdict()
+    t = time.perf_counter()
+    n_chunks, n_first, out = _oracle_pass(data, zd)
+    dt = time.perf_counter() - t
+    return {"value": data.size / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "first %d MiB of the same seed-42 corpus, oracle.chunk (NumPy) + hashlib + dict dedup + zlib-6 "
+                      "with the preset dictionary, %.1f s, %d chunks, %d unique" % (sample_mib, dt, n_chunks, n_first)}
+
+
+def _ref_worker(conn, slice_mib, idx):
+    """One oracle process: owns one slice of the corpus; phase 1 = chunk + digest, phase 2 = compress
+    the chunks the parent's global dedup kept."""
+    import numpy as np
+    import oracle
+    from oracle import corpus
+    data = corpus.generate(slice_mib << 20, first_article=idx * 997)
+    zd = corpus.zdict()
+    conn.send("ready")
+    cuts = None
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            return
+        if msg == "p1":
+            cuts = oracle.chunk(data)
+            conn.send(oracle.digest(data, cuts).tobytes())
+        else:
+            keep = np.frombuffer(msg, dtype=np.uint8).astype(bool)
+            blob, _ = oracle.compress(data, cuts, np.flatnonzero(keep), zd)
+            conn.send(blob.size)
+
+
+def run_reference(args):
+    """The oracle on every host core: workers chunk+digest their slice, the parent dedups
+    globally, workers compress their first occurrences.  Each step is a bounded sample."""
+    import multiprocessing as mp
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    slice_mib = 16
+    ctx = mp.get_context("spawn")
+    conns, ps = [], []
+    for i in range(procs):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(b, slice_mib, i), daemon=True)
+        p.start()
+        conns.append(a)
+        ps.append(p)
+    for c in conns:
+        assert c.recv() == "ready"
+
+    def step():
+        for c in conns:
+            c.send("p1")
+        digs = [c.recv() for c in conns]
+        alld = np.frombuffer(b"".join(digs), dtype=np.uint8).reshape(-1, 32)
+        _, first = oracle.dedup(alld)
+        pos = 0
+        for c, dbytes in zip(conns, digs):
+            k = len(dbytes) // 32
+            c.send(first[pos:pos + k].astype(np.uint8).tobytes())
+            pos += k
+        return sum(c.recv() for c in conns)
+
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t) / args.steps
+    for c in conns:
+        c.send(None)
+    for p in ps:
+        p.join(timeout=10)
+    nbytes = procs * (slice_mib << 20)
+    val = nbytes / dt / 1e9
+    sample = "%d oracle processes (os.cpu_count()=%s) x %d MiB slices of the seed-42 corpus per step" % (
+        procs, os.cpu_count(), slice_mib)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1] (10 GB templated-wiki, CDC+SHA-256 dedup+preset-dict DEFLATE), "
+                                   "CPU oracle on a bounded sample: " + sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+    import torch
+    import hmse_b200
+    from hmse_b200 import corpus as pcorpus
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: hmse_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = hmse_b200.Context(local)
+    lib = ctx.lib
+    dev = ctx.tdev
+    cfg = hmse_b200.CDCConfig()
+    shard = int(args.gb * 1e9)
+    shard -= shard % 16
+    total = shard * world
+    eof = rank == world - 1
+    n_avail = shard if eof else shard + cfg.max_size
+    gen = pcorpus.DeviceCorpus(ctx)
+    d = gen.generate(n_avail, byte_off=rank * shard)
+    zd = ctx.stage(pcorpus.zdict())
+    torch.cuda.synchronize()
+
+    if world > 1:
+        pipe = hmse_b200.ShardedIngest(ctx, cfg, zd)
+        run = lambda buf: pipe.run(buf, shard, eof)  # noqa: E731
+    else:
+        pipe = hmse_b200.Ingest(ctx, cfg, zd)
+        run = lambda buf: pipe.run(buf)  # noqa: E731
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    res = None
+    for _ in range(args.warmup):
+        res = run(d)
+    lib.hmse_timing(ctx.h, 1)
+    stage_names = ["scan", "resolve", "sha256", "dedup", "deflate", "pack"]
+    stage_ms = {k: 0.0 for k in stage_names}
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.hmse_launch_count(ctx.h)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = run(d)
+        f = C.c_float(0)
+        for i, k in enumerate(stage_names):   # event reads only; the stream is already drained by the API
+            if lib.hmse_timing_ms(ctx.h, i, C.byref(f)) == 0:
+                stage_ms[k] += f.value
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = (lib.hmse_launch_count(ctx.h) - launches0) // max(1, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    lib.hmse_timing(ctx.h, 0)
+    stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    value = total / (ms * 1e-3) / 1e9
+
+    # ---- pipeline facts for the roofline ---------------------------------------------------------
+    n_chunks = res.n_chunks
+    cuts = res.cuts
+    starts = torch.cat([torch.full((1,), res.entry, dtype=torch.int64, device=dev), cuts[:-1]])
+    lens = cuts - starts
+    sel_bytes = int(lens[res.select].sum()) if res.select.numel() else 0
+    out_bytes = int(res.blob.numel())
+    peak, peak_src = measured_peak()
+    defl_bytes = sel_bytes + out_bytes
+    defl_gbs = defl_bytes / (stage_ms["deflate"] * 1e-3) / 1e9 if stage_ms["deflate"] > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "deflate_traffic.json")) as f:
+            tj = json.load(f)
+            if abs(tj.get("gb", -1) - args.gb) < 1e-9:
+                traffic = tj.get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": "deflate_kernel (both size classes, one HT_DEFLATE event span per step)",
+                "achieved": defl_gbs, "peak": peak, "unit": "GB/s", "frac": defl_gbs / peak, "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": defl_bytes, "ms_per_launch": stage_ms["deflate"],
+                "other_kernels": {k: {"ms": stage_ms[k],
+                                      "GB/s": (shard / (stage_ms[k] * 1e-3) / 1e9) if stage_ms[k] > 0 else None}
+                                  for k in ("scan", "resolve", "sha256")},
+                "pipeline_frac": ((total + sum_over_ranks(out_bytes) + 40 * sum_over_ranks(n_chunks)) / (ms * 1e-3) / 1e9)
+                / (peak * world)}
+
+    # ---- end to end: pinned host input -> device -> results back on the host, every step ----------
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty(n_avail, dtype=torch.uint8, pin_memory=True)
+        host_in.copy_(d)
+        dbuf = ctx.empty(n_avail + 64, torch.uint8)[:n_avail]
+        cap_chunks = n_avail // cfg.min_size + 2
+        host_out = {"cuts": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
+                    "digests": torch.empty(cap_chunks * 32, dtype=torch.uint8, pin_memory=True),
+                    "canon": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
+                    "offsets": torch.empty(cap_chunks + 1, dtype=torch.int64, pin_memory=True),
+                    "blob": torch.empty(n_avail // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)}
+        d2h = 0
+
+        def e2e_step():
+            nonlocal d2h
+            dbuf.copy_(host_in, non_blocking=True)
+            r = run(dbuf)
+            nb = r.blob.numel()
+            if nb > host_out["blob"].numel():
+                host_out["blob"] = torch.empty(nb + (nb >> 3), dtype=torch.uint8, pin_memory=True)
+            host_out["cuts"][:r.n_chunks].copy_(r.cuts, non_blocking=True)
+            host_out["digests"][:r.n_chunks * 32].copy_(r.digests.view(-1), non_blocking=True)
+            host_out["canon"][:r.n_chunks].copy_(r.canon, non_blocking=True)
+            host_out["offsets"][:r.offsets.numel()].copy_(r.offsets, non_blocking=True)
+            host_out["blob"][:nb].copy_(r.blob, non_blocking=True)
+            d2h = r.n_chunks * (8 + 32 + 8) + r.offsets.numel() * 8 + nb
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_e2e = max(1, min(args.steps, 3))
+        a0.record()
+        for _ in range(k_e2e):
+            e2e_step()
+        a1.record()
+        barrier()
+        ems = max_over_ranks(a0.elapsed_time(a1)) / k_e2e
+        e2e = {"value": total / (ems * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(n_avail)),
+               "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": ems, "steps": k_e2e,
+               "api": "hmse_b200.Ingest.run on a device buffer filled from pinned host memory each step; cuts, digests, "
+                      "canon, offsets and the compressed blob copied back to pinned host memory each step"}
+        del host_in, host_out, dbuf
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.cpu_sample_mib)
+
+    uniq_chunks = sum_over_ranks(int(res.select.numel()))
+    tot_chunks = sum_over_ranks(n_chunks)
+    sel_b = sum_over_ranks(sel_bytes)
+    out_b = sum_over_ranks(out_bytes)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[1]: %.0f GB per GPU of seed-42 templated-wiki text generated on "
+                                       "the device, FastCDC avg 8 KiB (min 2 KiB, max 32 KiB) + SHA-256 + exact dedup + zlib-"
+                                       "format DEFLATE of first occurrences with a 30 KiB preset dictionary" % args.gb,
+                           "bytes_per_gpu": shard, "parallelism": "1 GPU" if world == 1 else
+                           "byte-range shards of one %d x %.0f GB stream, boundary resync + global dedup by NCCL all-to-all"
+                           % (world, args.gb),
+                           "l2": "inputs (%.0f GB per step) far exceed the 126 MB L2; no explicit flush" % args.gb,
+                           "chunks": int(tot_chunks), "unique_chunks": int(uniq_chunks),
+                           "unique_bytes": int(sel_b), "compressed_bytes": int(out_b),
+                           "compression_ratio_unique": (sel_b / out_b) if out_b else None},
+                "stages_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,13 +65,16 @@ def zdict(size: int = 32768) -> bytes:
     blob, off = lexicon()
     b = blob.tobytes()
     ent = [b[off[i]:off[i + 1]] for i in range(off.size - 1)]
-    frags = [ent[ID_WORD0 + i] for i in range(N_WORDS - 1, -1, -1)] + ent[:ID_WORD0]
-    seen, out = set(), []
-    for f in frags:
+    words, boiler, seen = [], [], set()
+    for f in (ent[ID_WORD0 + i] for i in range(N_WORDS - 1, -1, -1)):
         if f and f not in seen:
             seen.add(f)
-            out.append(f)
-    return b"".join(out)[-size:]
+            words.append(f)
+    for f in ent[:ID_WORD0]:
+        if f and f not in seen:
+            seen.add(f)
+            boiler.append(f)
+    return b"".join(words + boiler[::-1])[-size:]
 
 
 @dataclass(frozen=True)

@@ -439,9 +439,12 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
         HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)K1_SMEM));
         uint64_t grid = n_tiles < (uint64_t)ctx->sm_count ? n_tiles : (uint64_t)ctx->sm_count;
+        HT_BEGIN(ctx, HT_SCAN, st);
+        KL(ctx);
         gear_scan_kernel<<<(unsigned)grid, K1_THREADS, K1_SMEM, st>>>(
             d_data, n_avail, n_tiles, (const CdcDev*)ctx->slot[SLOT_CDC_CFG], bits, bits + words);
         HMSE_LAUNCH_CHECK(ctx);
+        HT_END(ctx, HT_SCAN, st);
     }
     ctx->cdc_have_scan = 1;
     return HMSE_OK;
@@ -500,7 +503,9 @@ HMSE_API int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n
                          ctx->n_seg == n_seg && ctx->seg_cap == seg_cap);
     int in = 0;
     int rounds = 0;
+    HT_BEGIN(ctx, HT_RESOLVE, st);
     if (fresh) {
+        KL(ctx);
         resolve_spec_kernel<<<wgrid, K2_THREADS, 0, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
     } else {
@@ -509,6 +514,7 @@ HMSE_API int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n
     volatile uint64_t* mail = ctx->pinned;
     for (;;) {
         HMSE_CUDA(ctx, cudaMemsetAsync(tail, 0, 8, st));
+        KL(ctx);
         resolve_fix_kernel<<<wgrid, K2_THREADS, 0, st>>>(a, in, (uint32_t*)tail);
         HMSE_LAUNCH_CHECK(ctx);
         HMSE_CUDA(ctx, cudaMemcpyAsync((void*)mail, tail, 8, cudaMemcpyDeviceToHost, st));
@@ -526,14 +532,17 @@ HMSE_API int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n
     ctx->n_seg = n_seg;
     ctx->seg_cap = seg_cap;
 
+    KL(ctx);
     seg_counts_kernel<<<(unsigned)div_up64(n_seg, 256), 256, 0, st>>>(meta, n_seg, counts);
     HMSE_LAUNCH_CHECK(ctx);
     int rc = hmse_exclusive_scan_u64(ctx, counts, offs, n_seg, tail + 1, st);
     if (rc) return rc;
     if (d_cuts && cap) {
+        KL(ctx);
         seg_gather_kernel<<<wgrid, K2_THREADS, 0, st>>>(a, offs, cap, d_cuts);
         HMSE_LAUNCH_CHECK(ctx);
     }
+    HT_END(ctx, HT_RESOLVE, st);
     HMSE_CUDA(ctx, cudaMemcpyAsync((void*)mail, tail + 1, 8, cudaMemcpyDeviceToHost, st));
     HMSE_CUDA(ctx, cudaMemcpyAsync((void*)(mail + 1), &meta[n_seg - 1].exit[in], 8, cudaMemcpyDeviceToHost, st));
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));

@@ -158,6 +158,7 @@ HMSE_API int hmse_corpus_lengths(hmse_ctx* ctx, const hmse_corpus_cfg* cfg, cons
     if (cfg->n_lex != ID_WORD0 + N_WORDS) HMSE_FAIL(ctx, HMSE_E_INVAL, "lexicon must have %u entries", ID_WORD0 + N_WORDS);
     if (first_article + n_articles > 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "article index exceeds 2^32");
     if (n_articles == 0) return HMSE_OK;
+    KL(ctx);
     corpus_lengths_kernel<<<(unsigned)div_up64(n_articles, 4), 128, 0, (cudaStream_t)stream>>>(
         *cfg, d_lex_off, first_article, n_articles, d_art_len);
     HMSE_LAUNCH_CHECK(ctx);
@@ -173,6 +174,7 @@ HMSE_API int hmse_corpus_render(hmse_ctx* ctx, const hmse_corpus_cfg* cfg, const
     if (cfg->n_lex != ID_WORD0 + N_WORDS) HMSE_FAIL(ctx, HMSE_E_INVAL, "lexicon must have %u entries", ID_WORD0 + N_WORDS);
     if (n_articles == 0 || n == 0) return HMSE_OK;
     const uint64_t cap = (uint64_t)ctx->sm_count * 8;
+    KL(ctx);
     corpus_render_kernel<<<(unsigned)(n_articles < cap ? n_articles : cap), RT, 0, (cudaStream_t)stream>>>(
         *cfg, d_lex_blob, d_lex_off, first_article, n_articles, d_art_off, byte_off, n, d_out);
     HMSE_LAUNCH_CHECK(ctx);

@@ -27,6 +27,11 @@ HMSE_API int hmse_create(int device, hmse_ctx** out) {
         delete c;
         return HMSE_E_CUDA;
     }
+    for (int i = 0; i < 2 * HT_COUNT; i++)
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) {
+            delete c;
+            return HMSE_E_CUDA;
+        }
     *out = c;
     return HMSE_OK;
 }
@@ -36,6 +41,8 @@ HMSE_API void hmse_destroy(hmse_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < SLOT_COUNT; i++)
         if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+    for (int i = 0; i < 2 * HT_COUNT; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     free(ctx->dict_host);
     delete ctx;
@@ -77,3 +84,21 @@ void* hmse_scratch(hmse_ctx* ctx, int slot, size_t bytes) {
     ctx->slot_bytes[slot] = want;
     return p;
 }
+
+HMSE_API int hmse_timing(hmse_ctx* ctx, int enable) {
+    if (!ctx) return HMSE_E_INVAL;
+    ctx->timing = enable;
+    memset(ctx->ev_set, 0, sizeof(ctx->ev_set));
+    return HMSE_OK;
+}
+
+HMSE_API int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms) {
+    if (!ctx || !ms || id < 0 || id >= HT_COUNT) return HMSE_E_INVAL;
+    *ms = 0.f;
+    if (!ctx->ev_set[id]) HMSE_FAIL(ctx, HMSE_E_INVAL, "timer %d has not been recorded", id);
+    HMSE_CUDA(ctx, cudaEventSynchronize(ctx->ev[2 * id + 1]));
+    HMSE_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[2 * id], ctx->ev[2 * id + 1]));
+    return HMSE_OK;
+}
+
+HMSE_API uint64_t hmse_launch_count(hmse_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -29,8 +29,17 @@ enum HmseSlot {
     SLOT_COUNT
 };
 
+// Timed regions (hmse_timing_ms ids; also in include/hmse.h)
+enum HmseTimer {
+    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_COUNT
+};
+
 struct hmse_ctx {
     int device;
+    cudaEvent_t ev[2 * HT_COUNT];
+    uint8_t ev_set[HT_COUNT];
+    int timing;
+    uint64_t launches;  // kernels launched through this ctx
     char err[512];
     void* slot[SLOT_COUNT];
     size_t slot_bytes[SLOT_COUNT];
@@ -66,6 +75,15 @@ struct hmse_ctx {
     } while (0)
 
 #define HMSE_LAUNCH_CHECK(ctx) HMSE_CUDA(ctx, cudaGetLastError())
+// counts a kernel launch; written before every <<< >>> so gpu_launches in bench.py is exact
+#define KL(ctx) ((ctx)->launches++)
+#define HT_BEGIN(ctx, id, st) \
+    if ((ctx)->timing) cudaEventRecord((ctx)->ev[2 * (id)], (st))
+#define HT_END(ctx, id, st)                                 \
+    if ((ctx)->timing) {                                    \
+        cudaEventRecord((ctx)->ev[2 * (id) + 1], (st));     \
+        (ctx)->ev_set[id] = 1;                              \
+    }
 
 #define HMSE_SCRATCH(ctx, var, type, slot, bytes)                  \
     type var = (type)hmse_scratch((ctx), (slot), (size_t)(bytes)); \

@@ -87,9 +87,13 @@ int run_table(hmse_ctx* ctx, const uint8_t* keys, uint64_t stride, uint64_t n, i
     HMSE_SCRATCH(ctx, table, uint32_t*, SLOT_DEDUP_TABLE, cap * sizeof(uint32_t));
     HMSE_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t), st));
     const unsigned grid = (unsigned)div_up64(n, 256);
+    HT_BEGIN(ctx, HT_DEDUP, st);
+    KL(ctx);
     dedup_insert_kernel<<<grid, 256, 0, st>>>(keys, stride, n, table, cap - 1);
+    KL(ctx);
     dedup_lookup_kernel<<<grid, 256, 0, st>>>(keys, stride, n, table, cap - 1, canon, is_first, canon_gid);
     HMSE_LAUNCH_CHECK(ctx);
+    HT_END(ctx, HT_DEDUP, st);
     return HMSE_OK;
 }
 
@@ -175,7 +179,45 @@ __global__ void read_gid_kernel(const uint8_t* __restrict__ records, uint64_t m,
     }
 }
 
+__global__ void flags_to_u64_kernel(const uint8_t* __restrict__ flags, uint64_t n, uint64_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = flags[i] ? 1ull : 0ull;
+}
+__global__ void select_scatter_kernel(const uint8_t* __restrict__ flags, const uint64_t* __restrict__ pos, uint64_t n,
+                                      uint64_t cap, uint64_t* __restrict__ select) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i] && pos[i] < cap) select[pos[i]] = i;
+}
+
 }  // namespace
+
+HMSE_API int hmse_dedup_select(hmse_ctx* ctx, const uint8_t* d_is_first, uint64_t n, uint64_t* d_select, uint64_t cap,
+                               uint64_t* m, void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!m) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_select: m is null");
+    *m = 0;
+    if (n == 0) return HMSE_OK;
+    if (!d_is_first) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_select: null pointer");
+    HMSE_SCRATCH(ctx, tmp, uint64_t*, SLOT_DEDUP_MISC, (n + 2) * 8);
+    const unsigned grid = (unsigned)div_up64(n, 256);
+    KL(ctx);
+    flags_to_u64_kernel<<<grid, 256, 0, st>>>(d_is_first, n, tmp);
+    HMSE_LAUNCH_CHECK(ctx);
+    int rc = hmse_exclusive_scan_u64(ctx, tmp, tmp, n, tmp + n, st);
+    if (rc) return rc;
+    if (d_select && cap) {
+        KL(ctx);
+        select_scatter_kernel<<<grid, 256, 0, st>>>(d_is_first, tmp, n, cap, d_select);
+        HMSE_LAUNCH_CHECK(ctx);
+    }
+    HMSE_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, tmp + n, 8, cudaMemcpyDeviceToHost, st));
+    HMSE_CUDA(ctx, cudaStreamSynchronize(st));
+    *m = ctx->pinned[0];
+    if (!d_select || *m > cap)
+        HMSE_FAIL(ctx, HMSE_E_CAPACITY, "d_select capacity %llu < %llu", (unsigned long long)cap, (unsigned long long)*m);
+    return HMSE_OK;
+}
 
 HMSE_API int hmse_dedup(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, int64_t* d_canon, uint8_t* d_is_first,
                           void* stream) {
@@ -200,11 +242,13 @@ HMSE_API int hmse_dedup_partition(hmse_ctx* ctx, const uint8_t* d_digests, uint6
     HMSE_SCRATCH(ctx, misc, uint64_t*, SLOT_DEDUP_MISC, 3 * (size_t)world * 8);
     HMSE_CUDA(ctx, cudaMemsetAsync(misc, 0, 3 * (size_t)world * 8, st));
     const unsigned grid = (unsigned)div_up64(n, 256);
+    KL(ctx);
     owner_hist_kernel<<<grid, 256, world * sizeof(unsigned int), st>>>(d_digests, n, world,
                                                                       (unsigned long long*)misc);
     HMSE_LAUNCH_CHECK(ctx);
     int rc = hmse_exclusive_scan_u64(ctx, misc, misc + world, world, nullptr, st);
     if (rc) return rc;
+    KL(ctx);
     owner_scatter_kernel<<<grid, 256, 0, st>>>(d_digests, n, id_base, world, misc + world,
                                                (unsigned long long*)(misc + 2 * world), d_records, d_perm);
     HMSE_LAUNCH_CHECK(ctx);
@@ -228,8 +272,11 @@ HMSE_API int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_
     unsigned long long* min_gid = (unsigned long long*)(table + cap);
     HMSE_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t) + m * sizeof(uint64_t), st));
     const unsigned grid = (unsigned)div_up64(m, 256);
+    KL(ctx);
     dedup_insert_kernel<<<grid, 256, 0, st>>>(d_records, 40, m, table, cap - 1);
+    KL(ctx);
     min_gid_kernel<<<grid, 256, 0, st>>>(d_records, m, table, cap - 1, min_gid);
+    KL(ctx);
     read_gid_kernel<<<grid, 256, 0, st>>>(d_records, m, table, cap - 1, min_gid, d_canon_gid);
     HMSE_LAUNCH_CHECK(ctx);
     return HMSE_OK;
@@ -240,6 +287,7 @@ HMSE_API int hmse_dedup_scatter(hmse_ctx* ctx, const uint64_t* d_reply, const ui
     if (!ctx) return HMSE_E_INVAL;
     if (n == 0) return HMSE_OK;
     if (!d_reply || !d_perm || !d_canon) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_scatter: null pointer");
+    KL(ctx);
     scatter_reply_kernel<<<(unsigned)div_up64(n, 256), 256, 0, (cudaStream_t)stream>>>(d_reply, d_perm, n, id_base,
                                                                                       d_canon, d_is_first);
     HMSE_LAUNCH_CHECK(ctx);

@@ -792,6 +792,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     uint64_t* d_tot = (uint64_t*)(counters + 4);  // [stage total, out total]
     d_tot = (uint64_t*)(((uintptr_t)d_tot + 7) & ~(uintptr_t)7);
     HMSE_CUDA(ctx, cudaMemsetAsync(list_n, 0, 64, st));
+    KL(ctx);
     classify_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(start0, d_cuts, d_select, m, slot_size, lists, list_n);
     HMSE_LAUNCH_CHECK(ctx);
     int rc = hmse_exclusive_scan_u64(ctx, slot_size, slot_off, m, d_tot, st);
@@ -825,12 +826,14 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     const uint32_t g_large = n_large < max_large ? n_large : max_large;
     HMSE_SCRATCH(ctx, work, uint32_t*, SLOT_DEFLATE_WORK,
                  ((size_t)g_small * NMAX_SMALL + (size_t)g_large * NMAX_LARGE) * 4 + 64);
+    HT_BEGIN(ctx, HT_DEFLATE, st);
     if (g_small) {
         a.list = lists;
         a.list_n = list_n;
         a.nmax = NMAX_SMALL;
         a.match = work;
         a.counter = counters;
+        KL(ctx);
         deflate_kernel<<<g_small, T_SMALL, sm_small, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
     }
@@ -840,15 +843,18 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         a.nmax = NMAX_LARGE;
         a.match = work + (size_t)g_small * NMAX_SMALL;
         a.counter = counters + 1;
+        KL(ctx);
         deflate_kernel<<<g_large, T_LARGE, sm_large, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
     }
     if (n_huge) {
         a.list = lists + 2 * m;
         a.list_n = list_n + 2;
+        KL(ctx);
         stored_kernel<<<n_huge < 1024 ? n_huge : 1024, 256, 0, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
     }
+    HT_END(ctx, HT_DEFLATE, st);
     HMSE_CUDA(ctx, cudaMemsetAsync(sizes + m, 0, 8, st));
     rc = hmse_exclusive_scan_u64(ctx, sizes, d_offsets, m + 1, d_tot + 1, st);
     if (rc) return rc;
@@ -859,7 +865,10 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         HMSE_FAIL(ctx, HMSE_E_CAPACITY, "d_out capacity %llu < %llu bytes", (unsigned long long)out_cap,
                   (unsigned long long)mail[0]);
     const uint64_t pg = m < (uint64_t)ctx->sm_count * 16 ? m : (uint64_t)ctx->sm_count * 16;
+    HT_BEGIN(ctx, HT_PACK, st);
+    KL(ctx);
     pack_kernel<<<(unsigned)pg, 256, 0, st>>>(stage, slot_off, d_offsets, m, d_out, out_cap);
     HMSE_LAUNCH_CHECK(ctx);
+    HT_END(ctx, HT_PACK, st);
     return HMSE_OK;
 }

@@ -177,6 +177,7 @@ HMSE_API int hmse_lsh_buckets(hmse_ctx* ctx, const uint64_t* d_keys, uint64_t n,
     uint32_t* iB = iA + total;
     HMSE_SCRATCH(ctx, hist, uint32_t*, SLOT_LSH_MISC, (size_t)bands * 256 * n_tiles * 4);
     const dim3 grid(n_tiles, bands);
+    HT_BEGIN(ctx, HT_LSH, st);
     for (uint32_t pass = 0; pass < 8; pass++) {
         SortArgs a;
         a.first = pass == 0;
@@ -193,10 +194,14 @@ HMSE_API int hmse_lsh_buckets(hmse_ctx* ctx, const uint64_t* d_keys, uint64_t n,
         a.bands = bands;
         a.n_tiles = n_tiles;
         a.shift = pass * 8;
+        KL(ctx);
         lsh_hist_kernel<<<grid, LT, 0, st>>>(a);
+        KL(ctx);
         lsh_scan_kernel<<<bands, LT, 0, st>>>(hist, n_tiles);
+        KL(ctx);
         lsh_scatter_kernel<<<grid, LT, 0, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
     }
+    HT_END(ctx, HT_LSH, st);
     return HMSE_OK;
 }

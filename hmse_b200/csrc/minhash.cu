@@ -96,9 +96,12 @@ int launch_minhash(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const 
     uint64_t blocks = div_up64(n_chunks, 4);
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
+    HT_BEGIN(ctx, HT_MINHASH, st);
+    KL(ctx);
     minhash_kernel<PER_LANE><<<(unsigned)blocks, 128, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_seeds, d_sig,
                                                                counter);
     HMSE_LAUNCH_CHECK(ctx);
+    HT_END(ctx, HT_MINHASH, st);
     return HMSE_OK;
 }
 
@@ -133,6 +136,7 @@ HMSE_API int hmse_lsh_keys(hmse_ctx* ctx, const uint32_t* d_sig, uint64_t n, uin
     if (bands == 0 || rows == 0) HMSE_FAIL(ctx, HMSE_E_INVAL, "bands and rows must be positive");
     if (n == 0) return HMSE_OK;
     if (!d_sig || !d_keys) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_lsh_keys: null pointer");
+    KL(ctx);
     lsh_keys_kernel<<<(unsigned)div_up64(n * bands, 256), 256, 0, (cudaStream_t)stream>>>(d_sig, n, bands, rows,
                                                                                          d_keys);
     HMSE_LAUNCH_CHECK(ctx);

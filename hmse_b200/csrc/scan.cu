@@ -93,8 +93,11 @@ int hmse_exclusive_scan_u64(hmse_ctx* ctx, const uint64_t* d_in, uint64_t* d_out
     uint64_t n_tiles = div_up64(n, SCAN_TILE);
     if (n_tiles == 0) n_tiles = 1;
     HMSE_SCRATCH(ctx, sums, uint64_t*, SLOT_SCAN, n_tiles * sizeof(uint64_t));
+    KL(ctx);
     scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>(d_in, n, sums);
+    KL(ctx);
     scan_sums<<<1, SCAN_THREADS, 0, stream>>>(sums, n_tiles, d_total);
+    KL(ctx);
     scan_apply<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>(d_in, d_out, n, sums);
     HMSE_LAUNCH_CHECK(ctx);
     return HMSE_OK;

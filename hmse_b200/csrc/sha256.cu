@@ -140,7 +140,10 @@ HMSE_API int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, 
     uint64_t blocks = div_up64(n_chunks, SHA_THREADS);
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
     if (blocks > max_blocks) blocks = max_blocks;
+    HT_BEGIN(ctx, HT_SHA, st);
+    KL(ctx);
     sha256_kernel<<<(unsigned)blocks, SHA_THREADS, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_digests, counter);
     HMSE_LAUNCH_CHECK(ctx);
+    HT_END(ctx, HT_SHA, st);
     return HMSE_OK;
 }

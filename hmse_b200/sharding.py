@@ -1,0 +1,77 @@
+"""Multi-GPU protocol of the hot path, independent of how the local work is
+computed so that it can be exercised with torch.distributed/gloo on CPU:
+
+* stitch_cuts       byte-range shards -> the single-stream cut list.  Every rank resolves its
+                    shard speculatively from offset 0, then the exit of rank r-1 (8 bytes) becomes
+                    the entry of rank r and the shard is re-resolved incrementally; repeated until
+                    no entry changes (chains converge within a few chunks, so normally one round).
+* exchange_dedup    global exact dedup: records {digest, gid} go to owner = le32(digest) % world
+                    with one all-to-all, the owner answers the smallest gid per digest with a
+                    second all-to-all (north_star: "GPU hash table partitioned by digest prefix
+                    with NCCL all-to-all over NVLink").
+One process per GPU; `dev` is the device the collectives' tensors live on (cuda for NCCL, cpu
+for gloo)."""
+from __future__ import annotations
+
+from typing import Callable, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def _all_gather_i64(value: int, dev, group=None) -> List[int]:
+    world = dist.get_world_size(group)
+    mine = torch.tensor([value], dtype=torch.int64, device=dev)
+    out = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [int(t.item()) for t in out]
+
+
+def stitch_cuts(resolve: Callable[[int], Tuple[object, int]], n_own: int, dev, group=None, max_rounds: int = 64):
+    """resolve(entry) -> (cuts, exit_off) over the local shard (exit_off relative to the shard
+    start; the next shard's entry is exit_off - n_own).  Returns (cuts, entry, rounds)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    entry = 0
+    cuts, exit_off = resolve(entry)
+    rounds = 0
+    for rounds in range(1, max_rounds + 1):
+        exits = _all_gather_i64(exit_off, dev, group)
+        owns = _all_gather_i64(n_own, dev, group)
+        new_entry = 0 if rank == 0 else max(0, exits[rank - 1] - owns[rank - 1])
+        changed = int(new_entry != entry)
+        if changed:
+            entry = new_entry
+            cuts, exit_off = resolve(entry)
+        if sum(_all_gather_i64(changed, dev, group)) == 0:
+            break
+    else:
+        raise RuntimeError("shard boundary resync did not converge in %d rounds" % max_rounds)
+    return cuts, entry, rounds
+
+
+def exchange_counts(counts: List[int], dev, group=None) -> List[int]:
+    """counts[o] = records this rank sends to owner o  ->  recv[r] = records arriving from rank r."""
+    world = dist.get_world_size(group)
+    send = torch.tensor(counts, dtype=torch.int64, device=dev)
+    recv = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, group=group)
+    return [int(x) for x in recv.tolist()]
+
+
+def all_to_all_bytes(send: torch.Tensor, send_counts: List[int], recv_counts: List[int], width: int, group=None):
+    """send: uint8 tensor of sum(send_counts)*width bytes grouped by destination rank."""
+    recv = torch.empty(sum(recv_counts) * width, dtype=torch.uint8, device=send.device)
+    dist.all_to_all_single(recv, send, [c * width for c in recv_counts], [c * width for c in send_counts], group=group)
+    return recv
+
+
+def exchange_dedup(records: torch.Tensor, counts: List[int], owner_resolve: Callable[[torch.Tensor, int], torch.Tensor],
+                   group=None) -> torch.Tensor:
+    """records: uint8[sum(counts)*40] grouped by owner.  owner_resolve(recv_records, m) -> int64[m]
+    canonical gid per received record.  Returns int64[sum(counts)] replies in send order."""
+    dev = records.device
+    recv_counts = exchange_counts(counts, dev, group)
+    recv = all_to_all_bytes(records, counts, recv_counts, 40, group)
+    answers = owner_resolve(recv, sum(recv_counts))
+    back = all_to_all_bytes(answers.view(torch.uint8), recv_counts, counts, 8, group)
+    return back.view(torch.int64)

@@ -59,6 +59,21 @@ const char* hmse_last_error(hmse_ctx* ctx);
 /* Bytes of device scratch currently held by ctx. */
 uint64_t hmse_scratch_bytes(hmse_ctx* ctx);
 
+/* ---- Measurement hooks (bench.py).  With timing enabled every entry point brackets its kernels
+ *      with CUDA events on `stream`; hmse_timing_ms returns the last recorded span of a region. -- */
+#define HMSE_T_SCAN 0
+#define HMSE_T_RESOLVE 1
+#define HMSE_T_SHA 2
+#define HMSE_T_DEDUP 3
+#define HMSE_T_DEFLATE 4
+#define HMSE_T_PACK 5
+#define HMSE_T_MINHASH 6
+#define HMSE_T_LSH 7
+int hmse_timing(hmse_ctx* ctx, int enable);
+int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms);
+/* Kernels launched through this ctx since hmse_create. */
+uint64_t hmse_launch_count(hmse_ctx* ctx);
+
 /* ---- L2 chunking: replaces rabin_slide + the boundary loop of benchmark_fastcdc
  *      (README.md:2456-2464, 2475-2490). ------------------------------------------------- */
 
@@ -95,6 +110,11 @@ int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uin
 /* d_canon[i] = smallest j with digest j == digest i; d_is_first[i] = (canon == i). */
 int hmse_dedup(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, int64_t* d_canon,
                uint8_t* d_is_first, void* stream);
+
+/* d_select[0..*m) = ascending indices i with d_is_first[i] != 0 (the chunks to store/compress).
+ * On HMSE_E_CAPACITY *m holds the required capacity. */
+int hmse_dedup_select(hmse_ctx* ctx, const uint8_t* d_is_first, uint64_t n, uint64_t* d_select, uint64_t cap,
+                      uint64_t* m, void* stream);
 
 /* Multi-GPU dedup, sender side: groups records {digest[32], gid u64} by owner = le32(digest) %
  * world into d_records (40 B each, owner-major), d_perm[k] = local index of record k,
