@@ -2,18 +2,25 @@
 // the skeleton's mz_deflateInit2(..., 15, ...) / mz_deflate(FINISH) at README.md:2374, 2378;
 // resolved to one RFC 1950 stream per chunk with FDICT in SURVEY.md §0.2 C5).
 //
-// One CTA compresses one chunk at a time (persistent CTAs pull chunks from a counter, two size
-// classes so small chunks get 3 CTAs per SM).  Unlike zlib's serial hash-chain walk, the best
-// match of EVERY position is found in parallel, then the zlib level-6 lazy rule is applied as a
-// pure function next(p) so the parse becomes chain following:
-//   P0 stage chunk into shared memory          P5 per-32-byte-range backward DP of chain exits
-//   P1 histogram of 4-byte hashes (13 bits)    P6 hop the true chain across ranges
-//   P2 scan -> bucket ends                     P7 symbol histograms of the visited tokens
-//   P3 scatter positions into buckets          P8 Huffman lengths/codes + dynamic header
-//   P4 match search: own buckets in shared,    P9 bit counts per range + block scan
-//      dictionary buckets (host-built index,   P10 parallel bit emission into the stage slot
-//      L1/L2 resident) in global memory        (stored / fixed / dynamic chosen like zlib)
-// A pack kernel then compacts the per-chunk stage slots into the caller's blob.
+// zlib walks hash chains serially; here the best match of EVERY position is found in parallel
+// and the zlib level-6 lazy rule becomes a pure function next(p), so the parse is chain
+// following.  Three kernels per batch of chunks, so that no phase leaves a CTA idle:
+//
+//  parse_kernel    one CTA per chunk (persistent, two size classes).
+//     P0 stage chunk in shared memory + Adler-32      P4 match search, one thread per SORTED index
+//     P1 histogram of 4-byte hashes (13 bits)            (lanes of a warp share a bucket: similar
+//     P2 scan -> bucket starts                            chain lengths, broadcast loads), own
+//     P3 tile-ordered scatter + bucket fix-up sort        buckets in shared memory, dictionary
+//        (positions ascending: nearest-first search,      buckets (host-built index) from L1/L2
+//        deterministic output)                         P5 per-32-byte-range backward DP of chain exits
+//                                                      P6 hop the true chain across ranges
+//                                                      P7 symbol histograms + compact u16 token stream
+//  huffman_kernel  one WARP per chunk: length-limited Huffman lengths (two-queue merge by lane 0,
+//                  everything else lane-parallel), canonical codes, dynamic header, block type
+//                  choice (stored / fixed / dynamic by exact cost, like zlib).
+//  encode_kernel   one CTA per chunk: token -> bit strings, block scan of bit counts, parallel
+//                  emission (atomicOr only on words shared by two threads), zlib header/trailer.
+//  pack_kernel     compacts the per-chunk stage slots into the caller's blob.
 // Output is compared with zlib by inflate-equality and total size only (never byte for byte).
 #include <stdlib.h>
 
@@ -24,18 +31,37 @@ using namespace dfl;
 
 namespace {
 
-constexpr int OWN_CAP = 48;    // own-chunk candidates examined per position
-constexpr int DICT_CAP = 32;   // dictionary candidates examined per position
+constexpr int OWN_CAP = 16;       // nearest own-chunk candidates examined per position
+constexpr int DICT_CAP = 8;       // nearest dictionary candidates examined per position (2 batches of 4)
 constexpr uint32_t DICT_MAX = 32768;
 constexpr uint32_t NMAX_SMALL = 12288, NMAX_LARGE = 32768;
-constexpr int T_SMALL = 256, T_LARGE = 512;
+constexpr int T_PARSE = 512;
+constexpr int T_ENCODE = 256;
+constexpr int HUFF_WARPS = 8;
+constexpr uint32_t BATCH_SMALL = 32768, BATCH_LARGE = 8192;  // chunks per batch (bounds the token scratch)
+constexpr uint32_t REC_WORDS = 320;                          // 288 lit/len + 32 dist counters / codes
 
 // Device image of the dictionary index (SLOT_DEFLATE_DICT), built on the host once per dictionary.
+struct DictEnt {   // 16 bytes: a match of up to 8 bytes is decided without touching the dictionary text
+    uint32_t first4;  // le32 at pos
+    uint32_t next4;   // le32 at pos + 4 (zero padded past the end)
+    uint32_t pos;
+    uint32_t pad;
+};
 struct DictDev {
     uint8_t bytes[DICT_MAX + 16];
-    uint16_t boff[NBUCKET + 8];   // bucket h = [boff[h], boff[h+1]) in sorted order
-    uint16_t sorted[DICT_MAX];    // positions, nearest (largest) first inside a bucket
-    uint32_t first4[DICT_MAX];    // le32 at the position, same order as sorted[]
+    uint16_t boff[NBUCKET + 8];  // bucket h = ent[boff[h] .. boff[h+1]), nearest (largest pos) first
+    DictEnt ent[DICT_MAX];
+};
+
+// Per-chunk record handed from kernel to kernel (indexed by job within the batch).
+struct ChunkRec {
+    uint32_t n;         // chunk length
+    uint32_t n_words;   // u16 token words
+    uint32_t adler;
+    uint32_t mode;      // 0 stored, 1 fixed, 2 dynamic
+    uint32_t hdr_bits;
+    uint32_t pad[3];
 };
 
 struct DeflArgs {
@@ -47,33 +73,37 @@ struct DeflArgs {
     uint32_t dict_len, dict_adler;
     int level;
     const uint32_t* list;    // selection slots of this size class
-    const uint32_t* list_n;
+    uint32_t job0, job1;     // batch = list[job0 .. job1)
     uint32_t nmax;
+    int match_smem;          // match words live in shared memory (small class) or in `match`
     uint8_t* stage;
     const uint64_t* slot_off;
     uint64_t* sizes;
-    uint32_t* match;         // per-CTA scratch, nmax words each
+    uint32_t* match;         // per-CTA scratch, nmax words each (large class)
+    uint16_t* tokens;        // [batch job][nmax] u16 words (<= one word per input byte)
+    uint32_t* hist;          // [batch job][REC_WORDS]: symbol counts, then canonical codes
+    uint8_t* hdrs;           // [batch job][640] dynamic header bytes
+    ChunkRec* recs;          // [batch job]
     unsigned int* counter;
 };
 
-// Per-phase cycle counters (thread 0 of every CTA, summed over chunks); read by
+// Per-phase cycle counters of parse_kernel (thread 0 of every CTA, summed over chunks); read by
 // hmse_debug_deflate_prof.  A dozen clock reads per chunk: negligible.
 __device__ unsigned long long g_prof[16];
-#define PROF(i)                                             \
-    if (t == 0) {                                           \
-        const long long now__ = clock64();                  \
+#define PROF(i)                                                     \
+    if (t == 0) {                                                   \
+        const long long now__ = clock64();                          \
         atomicAdd(&g_prof[i], (unsigned long long)(now__ - tprev)); \
-        tprev = now__;                                      \
+        tprev = now__;                                              \
     }
 
-struct Small {  // fixed-size shared state
-    uint32_t hist_lit[288];
-    uint32_t hist_dist[32];
-    uint32_t code_lit[288];
-    uint32_t code_dist[32];
+constexpr uint32_t CNT_WORDS = NBUCKET / 2 + 36;  // bucket table; later the 32 x 258 block-exit table
+
+struct ParseSm {  // fixed-size shared state of parse_kernel
+    uint32_t hist[REC_WORDS];
+    uint16_t bentry[32];
     uint32_t warp_tmp[40];
-    uint8_t hdr[640];
-    uint32_t hdr_bits, mode, total_bits, job, n_used;
+    uint32_t job, n_big;
     uint32_t adler_a, adler_b;
 };
 
@@ -116,28 +146,594 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, u
     return r;
 }
 
-// Token at p given the (lazy-resolved) match word: returns step, fills symbol info.
-struct Tok {
-    uint32_t step, lsym, lbits, lval, dsym, dbits, dval;
-    bool is_match;
-};
-__device__ __forceinline__ Tok token_at(uint32_t mw, uint32_t byte) {
-    Tok t;
-    const uint32_t L = mw >> 16;
-    if (L == 0 || (mw & 0x8000u)) {
-        t.is_match = false;
-        t.step = 1;
-        t.lsym = byte;
-        t.lbits = t.lval = t.dsym = t.dbits = t.dval = 0;
-    } else {
-        t.is_match = true;
-        t.step = L;
-        len_sym(L, t.lsym, t.lbits, t.lval);
-        dist_sym((mw & 0x7fffu) + 1, t.dsym, t.dbits, t.dval);
+// Common-prefix length of chunk[p+l ..] and chunk[q+l ..] continuing from l (both in shared memory).
+__device__ __forceinline__ uint32_t extend_own(const uint32_t* d32, uint32_t p, uint32_t q, uint32_t l, uint32_t lim) {
+    while (l < lim) {
+        const uint32_t x = ld32u(d32, p + l) ^ ld32u(d32, q + l);
+        if (x) {
+            l += (uint32_t)(__ffs((int)x) - 1) >> 3;
+            break;
+        }
+        l += 4;
     }
-    return t;
+    return l > lim ? lim : l;
+}
+__device__ __forceinline__ uint32_t extend_dict(const uint32_t* d32, const uint8_t* dict, uint32_t p, uint32_t j,
+                                                uint32_t l, uint32_t lim) {
+    while (l < lim) {
+        const uint32_t x = ld32u(d32, p + l) ^ ldg32u(dict, j + l);
+        if (x) {
+            l += (uint32_t)(__ffs((int)x) - 1) >> 3;
+            break;
+        }
+        l += 4;
+    }
+    return l > lim ? lim : l;
 }
 
+// Ascending bitonic sort of a[0..k) by one warp ("normalised" network: every compare-exchange
+// is ascending, so virtual +inf padding past k never moves).
+__device__ __forceinline__ void warp_sort_u16(uint16_t* a, uint32_t k, unsigned lane) {
+    uint32_t P = 2;
+    while (P < k) P <<= 1;
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t i = lane; i < P; i += 32) {
+            const uint32_t l = i ^ (size - 1);
+            if (l > i && l < k) {
+                const uint16_t x = a[i], y = a[l];
+                if (x > y) {
+                    a[i] = y;
+                    a[l] = x;
+                }
+            }
+        }
+        __syncwarp();
+        for (uint32_t j = size >> 2; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P; i += 32) {
+                const uint32_t l = i ^ j;
+                if (l > i && l < k) {
+                    const uint16_t x = a[i], y = a[l];
+                    if (x > y) {
+                        a[i] = y;
+                        a[l] = x;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Per-range passes touch element 32*r + j from lane r: a skew of one element per 32 makes those
+// accesses conflict free in shared memory.
+__device__ __forceinline__ uint32_t SK(uint32_t p) { return p + (p >> 5); }
+
+// Match word: bits 16..24 length (0 = literal), bit 15 "lazy: emit as literal", bits 0..14 distance-1.
+__device__ __forceinline__ bool mw_is_match(uint32_t mw) { return (mw >> 16) != 0 && !(mw & 0x8000u); }
+
+// =================================================================================================
+// parse_kernel
+// =================================================================================================
+__global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    const unsigned lane = t & 31, warp = t >> 5, nwarps = T >> 5;
+    const uint32_t nmax = a.nmax;
+    // layout
+    uint32_t* s_data32 = reinterpret_cast<uint32_t*>(smem);                     // nmax + 16 bytes
+    const uint8_t* s_data = smem;
+    uint16_t* s_sorted = reinterpret_cast<uint16_t*>(smem + nmax + 16);        // nmax u16 (later: exits, skewed)
+    uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + nmax + 16 + 2 * (size_t)(nmax + nmax / 32));  // CNT_WORDS
+    uint16_t* s_E = reinterpret_cast<uint16_t*>(s_cnt32);  // bucket h = sorted[E[h] .. E[h+1])
+    uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CNT_WORDS);         // nmax/32 bytes
+    uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_entry + nmax / 32);        // NBUCKET bits
+    ParseSm* sm = reinterpret_cast<ParseSm*>(s_flag + NBUCKET / 32);
+    uint8_t* s_tail = reinterpret_cast<uint8_t*>(sm) + ((sizeof(ParseSm) + 15) & ~15u);
+    // small class: match words in shared memory (skewed); the list of buckets to sort borrows that
+    // space before P4.  large class: match words in global scratch, the list has its own space.
+    uint32_t* mptr = a.match_smem ? reinterpret_cast<uint32_t*>(s_tail) : a.match + (size_t)blockIdx.x * (nmax + nmax / 32);
+    uint16_t* s_big = reinterpret_cast<uint16_t*>(s_tail);
+    uint16_t* s_exit = s_sorted;
+
+    for (;;) {
+        __syncthreads();
+        if (t == 0) sm->job = a.job0 + atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const uint32_t job = sm->job;
+        if (job >= a.job1) break;
+        long long tprev = clock64();
+        const uint32_t bj = job - a.job0;  // index inside the batch
+        const uint32_t k = a.list[job];
+        const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
+        const uint64_t cs = j ? a.cuts[j - 1] : a.start0;
+        const uint32_t n = (uint32_t)(a.cuts[j] - cs);
+        const uint8_t* src = a.data + cs;
+
+        // ---- P0: stage the chunk (byte-unaligned source -> aligned words), clear tables -----
+        {
+            const uint32_t kmis = (uint32_t)((uintptr_t)src & 3);
+            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(src - kmis);
+            const uint32_t nw = (n + 3) >> 2;
+            for (uint32_t i = t; i < nw + 4 && i < (nmax + 16) / 4; i += T) {
+                uint32_t v = 0;
+                if (i < nw) {
+                    uint32_t lo = __ldg(wsrc + i);
+                    uint32_t hi = kmis ? __ldg(wsrc + i + 1) : 0u;
+                    v = __funnelshift_r(lo, hi, kmis * 8);
+                    const uint32_t rem = n - 4 * i;  // bytes of this word inside the chunk
+                    if (rem < 4) v &= (1u << (8 * rem)) - 1;
+                }
+                s_data32[i] = v;
+            }
+            for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;
+            for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
+            if (t == 0) sm->n_big = 0;
+        }
+        __syncthreads();
+        PROF(0)
+        const uint32_t nh = n >= 4 ? n - 3 : 0;  // hashed positions
+
+        // ---- Adler-32 of the chunk (parallel partial sums, n <= 32768) --------------------
+        {
+            uint32_t sa = 0, sb = 0;
+            for (uint32_t p = t; p < n; p += T) {
+                uint32_t b = s_data[p];
+                sa += b;
+                sb += (n - p) * b;  // <= 32768*255 per term, <= 64 terms per thread
+                if (sb >= 0x80000000u) sb %= 65521u;
+            }
+            sb %= 65521u;
+            uint32_t tot_a, tot_b;
+            block_excl_scan(sa, sm->warp_tmp, &tot_a);
+            block_excl_scan(sb, sm->warp_tmp, &tot_b);
+            if (t == 0) {
+                sm->adler_a = (1u + tot_a) % 65521u;
+                sm->adler_b = (n % 65521u + tot_b) % 65521u;
+            }
+        }
+        PROF(1)
+        uint32_t n_words = 0;
+        if (a.level != 0) {
+            // ---- P1: hash histogram (count of bucket h lives at E[h+1]) ----------------------------
+            for (uint32_t p = t; p < nh; p += T) {
+                const uint32_t h1 = hash4(ld32u(s_data32, p)) + 1;
+                atomicAdd(&s_cnt32[h1 >> 1], 1u << (16 * (h1 & 1)));
+            }
+            __syncthreads();
+            // ---- P2: exclusive scan: E[h+1] = start of bucket h (cursor), E[0] = 0 ------------------
+            const uint32_t per = NBUCKET / T;  // buckets per thread (T divides NBUCKET)
+            {
+                uint32_t sum = 0;
+                for (uint32_t i = 0; i < per; i++) sum += s_E[t * per + i + 1];
+                uint32_t tot;
+                uint32_t run = block_excl_scan(sum, sm->warp_tmp, &tot);
+                for (uint32_t i = 0; i < per; i++) {
+                    const uint32_t c = s_E[t * per + i + 1];
+                    s_E[t * per + i + 1] = (uint16_t)run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            PROF(2)
+            // ---- P3: scatter tile by tile (cursors count up to the bucket ends): buckets end up
+            //      ordered by position except inside a tile, then every bucket is put in order ----
+            for (uint32_t p0 = 0; p0 < nh; p0 += T) {
+                const uint32_t p = p0 + t;
+                if (p < nh) {
+                    const uint32_t h1 = hash4(ld32u(s_data32, p)) + 1;
+                    const uint32_t sh = 16 * (h1 & 1);
+                    const uint32_t old = atomicAdd(&s_cnt32[h1 >> 1], 1u << sh);
+                    s_sorted[(old >> sh) & 0xffffu] = (uint16_t)p;
+                }
+                __syncthreads();
+            }
+            PROF(3)
+            // Buckets are already ordered except for same-hash positions inside one scatter tile.  Every
+            // adjacent pair is checked in parallel; only buckets with an inversion are sorted.
+            for (uint32_t i = t; i < NBUCKET / 32; i += T) s_flag[i] = 0;
+            __syncthreads();
+            for (uint32_t i = t + 1; i < nh; i += T) {
+                const uint32_t q0 = s_sorted[i - 1], q1 = s_sorted[i];
+                if (q0 > q1) {
+                    const uint32_t h = hash4(ld32u(s_data32, q1));
+                    if (i > s_E[h]) {  // same bucket: a real inversion
+                        const uint32_t old = atomicOr(&s_flag[h >> 5], 1u << (h & 31));
+                        if (!(old & (1u << (h & 31)))) s_big[atomicAdd(&sm->n_big, 1u)] = (uint16_t)h;
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = warp; i < sm->n_big; i += nwarps) {
+                const uint32_t h = s_big[i];
+                const uint32_t b0 = s_E[h];
+                warp_sort_u16(s_sorted + b0, (uint32_t)s_E[h + 1] - b0, lane);
+            }
+            __syncthreads();
+            PROF(4)
+            if (t < 3 && t < n) mptr[SK(n - 1 - t)] = 0;  // the last 3 positions cannot start a match
+            // ---- P4: best match of every position.  One thread per SORTED index: the lanes of a
+            //      warp work on the same or neighbouring buckets (similar chain lengths, broadcast
+            //      loads).  Nearest candidate first, strictly longer wins (zlib's rule).  Dictionary
+            //      loads run two positions ahead (bucket bounds) and one ahead (first 4 entries), so
+            //      their L2 latency overlaps the shared-memory search of the current position. -------
+            {
+                const uint4* ent = reinterpret_cast<const uint4*>(a.dict->ent);
+                const bool use_dict = a.dict_len != 0;
+                struct StA { uint32_t p, v, h, d0, d1; };
+                auto stageA = [&](uint32_t i) {
+                    StA r;
+                    r.p = 0xffffffffu; r.v = 0; r.h = 0; r.d0 = 0; r.d1 = 0;
+                    if (i < nh) {
+                        r.p = s_sorted[i];
+                        r.v = ld32u(s_data32, r.p);
+                        r.h = hash4(r.v);
+                        if (use_dict) {
+                            r.d0 = __ldg(&a.dict->boff[r.h]);
+                            r.d1 = __ldg(&a.dict->boff[r.h + 1]);
+                        }
+                    }
+                    return r;
+                };
+                StA s0 = stageA(t), s1 = stageA(t + T);
+                uint4 e1[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) e1[u] = s0.d0 + u < s0.d1 ? __ldg(ent + s0.d0 + u) : make_uint4(~s0.v, 0, 0, 0);
+                for (uint32_t i = t; i < nh; i += T) {
+                    const StA cur = s0;
+                    uint4 e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) e[u] = e1[u];
+                    s0 = s1;
+                    s1 = stageA(i + 2 * T);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) e1[u] = s0.d0 + u < s0.d1 ? __ldg(ent + s0.d0 + u) : make_uint4(~s0.v, 0, 0, 0);
+
+                    const uint32_t p = cur.p, v = cur.v, h = cur.h;
+                    const uint32_t maxl = n - p < (uint32_t)MAX_MATCH ? n - p : (uint32_t)MAX_MATCH;
+                    const uint32_t b0 = s_E[h];
+                    uint32_t best = 3, bdist = 0;
+                    const uint32_t stop = i > b0 + OWN_CAP ? i - OWN_CAP : b0;
+                    for (uint32_t c = i; c-- > stop;) {
+                        const uint32_t q = s_sorted[c];
+                        if (ld32u(s_data32, q) != v) continue;
+                        const uint32_t l = extend_own(s_data32, p, q, 4, maxl);
+                        if (l > best) {
+                            best = l;
+                            bdist = p - q;
+                            if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
+                        }
+                    }
+                    if (use_dict && best < (uint32_t)NICE_LENGTH && best < maxl) {
+                        const uint32_t nx = ld32u(s_data32, p + 4);
+                        bool done = false;
+                        for (uint32_t bi = cur.d0; bi < cur.d1 && bi < cur.d0 + DICT_CAP && !done; bi += 4) {
+                            if (bi != cur.d0) {
+#pragma unroll
+                                for (int u = 0; u < 4; u++) e[u] = bi + u < cur.d1 ? __ldg(ent + bi + u) : make_uint4(~v, 0, 0, 0);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (done || e[u].x != v) continue;
+                                const uint32_t jpos = e[u].z;
+                                const uint32_t dist = p + a.dict_len - jpos;
+                                if (dist > (uint32_t)WSIZE) {  // farther entries are only farther
+                                    done = true;
+                                    continue;
+                                }
+                                uint32_t lim = a.dict_len - jpos;  // matches do not run from the dictionary into the chunk
+                                if (lim > maxl) lim = maxl;
+                                const uint32_t x = e[u].y ^ nx;
+                                uint32_t l = x ? 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3) : 8;
+                                if (l > lim) l = lim;
+                                if (l == 8 && lim > 8) l = extend_dict(s_data32, a.dict->bytes, p, jpos, 8, lim);
+                                if (l > best) {
+                                    best = l;
+                                    bdist = dist;
+                                    if (best >= (uint32_t)NICE_LENGTH || best == maxl) done = true;
+                                }
+                            }
+                        }
+                    }
+                    mptr[SK(p)] = best >= 4 ? (best << 16) | (bdist - 1) : 0u;
+                }
+            }
+            __syncthreads();
+            PROF(5)
+
+            // ranges of 32 positions, blocked over threads
+            const uint32_t R = (n + 31) >> 5;
+            const uint32_t rpt = (R + T - 1) / T;
+            const uint32_t r0 = t * rpt, r1 = (r0 + rpt < R) ? r0 + rpt : R;
+            // ---- P5: backward DP: exit[p] = first chain position past p's range -------------
+            for (uint32_t r = r0; r < r1; r++) {
+                const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
+                uint32_t nxt_len = pe < n ? (mptr[SK(pe)] >> 16) : 0;
+                for (uint32_t p = pe; p-- > ps;) {
+                    const uint32_t mw = mptr[SK(p)];
+                    const uint32_t L = mw >> 16;
+                    const bool lazy_lit = L != 0 && L < (uint32_t)MAX_LAZY && nxt_len > L;
+                    if (lazy_lit) mptr[SK(p)] = mw | 0x8000u;
+                    const uint32_t next = (L == 0 || lazy_lit) ? p + 1 : p + L;
+                    s_exit[SK(p)] = (uint16_t)(next >= pe ? next : s_exit[SK(next)]);
+                    nxt_len = L;
+                }
+            }
+            for (uint32_t r = t; r < R; r += T) s_entry[r] = 0xFF;
+            __syncthreads();
+            PROF(6)
+            // ---- P6: hop the true chain across ranges, two levels.  A warp owns a block of 32 ranges
+            //      (1024 bytes).  (a) lane e follows the chain that enters the block's first ranges at
+            //      the e-th possible position and records where it leaves the block; (b) one thread
+            //      hops block to block through those tables; (c) lane 0 of every warp re-walks its block
+            //      from the true entry and marks the per-range entries. -----------------------------------
+            {
+                uint16_t* s_bexit = s_E;          // [block][258]: exit of a chain entering the block at offset o (E is dead)
+                uint16_t* s_bentry = sm->bentry;  // [block]: true entry position (0xFFFF = not visited)
+                const uint32_t NB = (n + 1023) >> 10;
+                // (a) entries into a block lie in its first 258 positions (a match is <= 258 long)
+                for (uint32_t blk = warp; blk < NB; blk += nwarps) {
+                    const uint32_t bs = blk << 10, be = (bs + 1024 < n) ? bs + 1024 : n;
+                    for (uint32_t o = lane; o < 258 && bs + o < be; o += 32) {
+                        uint32_t p = bs + o;
+                        while (p < be) p = s_exit[SK(p)];
+                        s_bexit[blk * 258 + o] = (uint16_t)p;
+                    }
+                    if (lane == 0) s_bentry[blk] = 0xFFFF;
+                }
+                __syncthreads();
+                if (t == 0) {  // (b)
+                    uint32_t p = 0;
+                    while (p < n) {
+                        const uint32_t blk = p >> 10;
+                        s_bentry[blk] = (uint16_t)p;
+                        p = s_bexit[blk * 258 + (p & 1023)];
+                    }
+                }
+                __syncthreads();
+                for (uint32_t blk = warp; blk < NB; blk += nwarps) {  // (c)
+                    if (lane == 0 && s_bentry[blk] != 0xFFFF) {
+                        const uint32_t be = ((blk << 10) + 1024 < n) ? (blk << 10) + 1024 : n;
+                        uint32_t p = s_bentry[blk];
+                        while (p < be) {
+                            s_entry[p >> 5] = (uint8_t)(p & 31);
+                            p = s_exit[SK(p)];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            PROF(7)
+            // ---- P7: symbol histograms + token words (literal: byte; match: 0x8000|len, dist-1) ----
+            uint32_t words = 0;
+            for (uint32_t r = r0; r < r1; r++) {
+                const uint32_t e = s_entry[r];
+                if (e == 0xFF) continue;
+                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
+                for (uint32_t p = (r << 5) + e; p < pe;) {
+                    const uint32_t mw = mptr[SK(p)];
+                    if (mw_is_match(mw)) {
+                        uint32_t sy, eb, ev;
+                        len_sym(mw >> 16, sy, eb, ev);
+                        atomicAdd(&sm->hist[sy], 1u);
+                        dist_sym((mw & 0x7fffu) + 1, sy, eb, ev);
+                        atomicAdd(&sm->hist[288 + sy], 1u);
+                        words += 2;
+                        p += mw >> 16;
+                    } else {
+                        atomicAdd(&sm->hist[s_data[p]], 1u);
+                        words += 1;
+                        p += 1;
+                    }
+                }
+            }
+            uint32_t w_off = block_excl_scan(words, sm->warp_tmp, &n_words);
+            uint16_t* tk = a.tokens + (size_t)bj * nmax;
+            for (uint32_t r = r0; r < r1; r++) {
+                const uint32_t e = s_entry[r];
+                if (e == 0xFF) continue;
+                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
+                for (uint32_t p = (r << 5) + e; p < pe;) {
+                    const uint32_t mw = mptr[SK(p)];
+                    if (mw_is_match(mw)) {
+                        tk[w_off++] = (uint16_t)(0x8000u | (mw >> 16));
+                        tk[w_off++] = (uint16_t)(mw & 0x7fffu);
+                        p += mw >> 16;
+                    } else {
+                        tk[w_off++] = s_data[p];
+                        p += 1;
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = t; i < REC_WORDS; i += T)
+                a.hist[(size_t)bj * REC_WORDS + i] = sm->hist[i] + (i == (uint32_t)EOB ? 1u : 0u);
+        }
+        if (t == 0) {
+            ChunkRec rec;
+            rec.n = n;
+            rec.n_words = n_words;
+            rec.adler = (sm->adler_b << 16) | sm->adler_a;
+            rec.mode = a.level == 0 ? 0u : 2u;
+            rec.hdr_bits = 0;
+            rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+            a.recs[bj] = rec;
+        }
+        PROF(8)
+        if (t == 0) atomicAdd(&g_prof[15], 1ull);
+    }
+}
+
+// =================================================================================================
+// huffman_kernel: one warp per chunk
+// =================================================================================================
+struct HuffSm {
+    uint32_t freq[REC_WORDS];
+    uint32_t codes[REC_WORDS];
+    HuffWork hw;
+    HuffWorkSmall hw2;
+    DynHeader dh;
+    uint8_t hdr[640];
+    uint32_t bl32[16];
+    uint32_t n_used, cost_dyn, cost_fix, mode, hdr_bits;
+    unsigned long long kraft;
+};
+
+__global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    HuffSm& s = reinterpret_cast<HuffSm*>(smem)[warp];
+    const uint32_t n_jobs = a.job1 - a.job0;
+    for (uint32_t bj = blockIdx.x * HUFF_WARPS + warp; bj < n_jobs; bj += gridDim.x * HUFF_WARPS) {
+        ChunkRec rec = a.recs[bj];
+        if (rec.mode == 0) continue;  // level 0: stored, nothing to build
+        uint32_t* g = a.hist + (size_t)bj * REC_WORDS;
+        uint32_t used = 0;
+        for (uint32_t i = lane; i < REC_WORDS; i += 32) {
+            const uint32_t f = g[i];
+            s.freq[i] = f;
+            s.codes[i] = 0;
+            used += (i < (uint32_t)NLIT) && f != 0;
+        }
+        if (lane < 16) s.bl32[lane] = 0;
+        if (lane == 0) {
+            s.cost_dyn = 0;
+            s.cost_fix = 0;
+            s.kraft = 0;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+        __syncwarp();
+        if (used < 2) {  // EOB is always used; force a second code like zlib (trees.c build_tree)
+            if (lane == 0) s.freq[s.freq[0] ? 1 : 0] = 1;
+            used = 2;
+            __syncwarp();
+        }
+        const uint32_t k_used = used;
+        // rank sort of the literal/length alphabet by (freq, symbol)
+        for (uint32_t sy = lane; sy < (uint32_t)NLIT; sy += 32) {
+            const uint32_t f = s.freq[sy];
+            s.dh.lit_lens[sy] = 0;
+            if (f) {
+                uint32_t rank = 0;
+                for (uint32_t o = 0; o < (uint32_t)NLIT; o++) {
+                    const uint32_t gq = s.freq[o];
+                    rank += (gq != 0) && (gq < f || (gq == f && o < sy));
+                }
+                s.hw.w[rank] = f;
+                s.hw.order[rank] = (uint16_t)sy;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) huff_merge(s.hw, (int)k_used);
+        if (lane == 1) {  // the distance tree is small: one lane, concurrently with the merge
+            uint32_t df[32];
+            for (int q = 0; q < 32; q++) df[q] = s.freq[288 + q];
+            build_lengths(df, NDIST, 15, s.dh.dist_lens, s.hw2);
+        }
+        __syncwarp();
+        {   // leaf depths by walking parents
+            const uint32_t root = 2 * k_used - 2;
+            for (uint32_t i = lane; i < k_used; i += 32) {
+                uint32_t node = i, dpt = 0;
+                while (node != root) {
+                    node = s.hw.parent[node];
+                    dpt++;
+                }
+                if (dpt > 15) dpt = 15;
+                atomicAdd(&s.bl32[dpt], 1u);
+                atomicAdd(&s.kraft, 1ull << (15 - dpt));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int b = 0; b < 16; b++) s.hw.bl_count[b] = (uint16_t)s.bl32[b];
+            huff_fix_overflow(s.hw.bl_count, 15, s.kraft);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < k_used; i += 32) {  // rarest leaves take the longest codes
+            uint32_t cum = 0, L = 1;
+            for (int bits = 15; bits >= 1; bits--) {
+                cum += s.hw.bl_count[bits];
+                if (i < cum) {
+                    L = (uint32_t)bits;
+                    break;
+                }
+            }
+            s.dh.lit_lens[s.hw.order[i]] = (uint8_t)L;
+        }
+        __syncwarp();
+        if (lane == 0) plan_header_from_lengths(s.dh, s.hw);  // RLE + code-length code (serial, small)
+        // canonical codes + block cost (lanes 1..31; lane 0 is busy with the header plan)
+        if (lane) {
+            uint32_t cd = 0, cf = 0;
+            for (uint32_t q = lane - 1; q < (uint32_t)NLIT + NDIST; q += 31) {
+                const bool is_dist = q >= (uint32_t)NLIT;
+                const uint32_t sy = is_dist ? q - NLIT : q;
+                const uint8_t* lens = is_dist ? s.dh.dist_lens : s.dh.lit_lens;
+                const uint32_t nsy = is_dist ? NDIST : NLIT;
+                const uint32_t l = lens[sy];
+                uint32_t code = 0;
+                if (l) {
+                    uint32_t nc = 0, same_before = 0;
+                    for (uint32_t o = 0; o < nsy; o++) {
+                        const uint32_t lo_ = lens[o];
+                        if (lo_ && lo_ < l) nc += 1u << (l - lo_);  // next_code[l] = sum count[b] << (l-b), b < l
+                        same_before += (lo_ == l) && (o < sy);
+                    }
+                    code = (l << 16) | bitrev(nc + same_before, (int)l);
+                }
+                const uint32_t f = g[is_dist ? 288 + sy : sy];  // true counts (without the forced code)
+                const uint32_t xb = is_dist ? (uint32_t)dsym_extra((int)sy) : (sy > 256 ? (uint32_t)lsym_extra((int)sy) : 0u);
+                cd += f * (l + xb);
+                cf += f * ((is_dist ? 5u : (uint32_t)fixed_lit_len((int)sy)) + xb);
+                s.codes[is_dist ? 288 + sy : sy] = code;
+            }
+            if (cd) atomicAdd(&s.cost_dyn, cd);
+            if (cf) atomicAdd(&s.cost_fix, cf);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const uint64_t dyn_bits = (uint64_t)s.dh.bits + s.cost_dyn, fix_bits = 3ull + s.cost_fix;
+            uint32_t mode = dyn_bits < fix_bits ? 2u : 1u;
+            const uint64_t best_bits = dyn_bits < fix_bits ? dyn_bits : fix_bits;
+            if ((uint64_t)rec.n + 5 <= (best_bits + 7) / 8) mode = 0;
+            BitWriter bw;
+            bw.buf = s.hdr;
+            bw.bitpos = 0;
+            if (mode == 2) {
+                write_dynamic_header(s.dh, bw, 1);
+            } else if (mode == 1) {
+                bw.put(1, 1);
+                bw.put(1, 2);
+            }
+            bw.finish();
+            s.mode = mode;
+            s.hdr_bits = (uint32_t)bw.bitpos;
+        }
+        __syncwarp();
+        const uint32_t mode = s.mode;
+        if (mode == 1) {
+            for (uint32_t i = lane; i < 288; i += 32) s.codes[i] = fixed_lit_code((int)i);
+            s.codes[288 + lane] = fixed_dist_code((int)lane);
+            __syncwarp();
+        }
+        for (uint32_t i = lane; i < REC_WORDS; i += 32) g[i] = s.codes[i];
+        if (mode != 0) {
+            const uint32_t hb = (s.hdr_bits + 7) >> 3;
+            uint8_t* gh = a.hdrs + (size_t)bj * 640;
+            for (uint32_t i = lane; i < hb; i += 32) gh[i] = s.hdr[i];
+        }
+        if (lane == 0) {
+            a.recs[bj].mode = mode;
+            a.recs[bj].hdr_bits = s.hdr_bits;
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// encode_kernel: one CTA per chunk
+// =================================================================================================
 struct Emitter {
     uint32_t* out;      // 4-byte aligned start of the deflate bit stream
     uint64_t acc;
@@ -167,370 +763,113 @@ struct Emitter {
     }
 };
 
-__global__ void __launch_bounds__(T_LARGE) deflate_kernel(DeflArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t T = blockDim.x, t = threadIdx.x;
-    const uint32_t nmax = a.nmax;
-    // layout
-    uint32_t* s_data32 = reinterpret_cast<uint32_t*>(smem);                     // nmax + 16 bytes
-    const uint8_t* s_data = smem;
-    uint16_t* s_sorted = reinterpret_cast<uint16_t*>(smem + nmax + 16);        // nmax u16 (later: exits)
-    uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + nmax + 16 + 2 * (size_t)nmax);  // NBUCKET/2 + 4 words
-    uint16_t* s_cnt16 = reinterpret_cast<uint16_t*>(s_cnt32);
-    uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + NBUCKET / 2 + 4);   // nmax/32 bytes
-    Small* sm = reinterpret_cast<Small*>(s_entry + nmax / 32);
-    // Huffman scratch aliases the bucket table (dead after P4)
-    HuffWork* hw = reinterpret_cast<HuffWork*>(s_cnt32);
-    DynHeader* dh = reinterpret_cast<DynHeader*>(reinterpret_cast<uint8_t*>(s_cnt32) + ((sizeof(HuffWork) + 15) & ~15u));
-    uint16_t* s_exit = s_sorted;
-    uint32_t* g_match = a.match + (size_t)blockIdx.x * nmax;
-    const uint32_t list_n = *a.list_n;
+// Bit string of token word w (prev = the word before it): value and length (<= 28 bits).
+__device__ __forceinline__ void word_bits(const uint32_t* codes, uint32_t w, uint32_t prev, uint32_t& val, uint32_t& nb) {
+    uint32_t sy, eb, ev, c;
+    if (prev & 0x8000u) {            // distance word of a match
+        dist_sym(w + 1, sy, eb, ev);
+        c = codes[288 + sy];
+    } else if (w & 0x8000u) {        // length word of a match
+        len_sym(w & 0x1ffu, sy, eb, ev);
+        c = codes[sy];
+    } else {                         // literal
+        c = codes[w];
+        eb = 0;
+        ev = 0;
+    }
+    const uint32_t cl = c >> 16;
+    val = (c & 0xffffu) | (ev << cl);
+    nb = cl + eb;
+}
 
-    for (;;) {
+__global__ void __launch_bounds__(T_ENCODE) encode_kernel(DeflArgs a) {
+    __shared__ uint32_t s_codes[REC_WORDS];
+    __shared__ uint32_t s_tmp[40];
+    __shared__ uint32_t s_hdr[160];
+    const uint32_t T = T_ENCODE, t = threadIdx.x;
+    const uint32_t n_jobs = a.job1 - a.job0;
+    for (uint32_t bj = blockIdx.x; bj < n_jobs; bj += gridDim.x) {
         __syncthreads();
-        if (t == 0) sm->job = atomicAdd(a.counter, 1u);
-        __syncthreads();
-        const uint32_t job = sm->job;
-        if (job >= list_n) break;
-        long long tprev = clock64();
-        const uint32_t k = a.list[job];
-        const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
-        const uint64_t cs = j ? a.cuts[j - 1] : a.start0;
-        const uint32_t n = (uint32_t)(a.cuts[j] - cs);
-        const uint8_t* src = a.data + cs;
+        const ChunkRec rec = a.recs[bj];
+        const uint32_t k = a.list[a.job0 + bj];
         uint8_t* slot = a.stage + a.slot_off[k];
         const uint32_t hdr_len = a.dict_len ? 6 : 2;
         uint32_t* out32 = reinterpret_cast<uint32_t*>(slot + 2 + hdr_len);  // slot is 16-aligned: 4 or 8
-
-        // ---- P0: stage the chunk (byte-unaligned source -> aligned words), clear tables -----
-        {
-            const uint32_t kmis = (uint32_t)((uintptr_t)src & 3);
-            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(src - kmis);
-            const uint32_t nw = (n + 3) >> 2;
-            for (uint32_t i = t; i < nw + 4 && i < (nmax + 16) / 4; i += T) {
-                uint32_t v = 0;
-                if (i < nw) {
-                    uint32_t lo = __ldg(wsrc + i);
-                    uint32_t hi = kmis ? __ldg(wsrc + i + 1) : 0u;
-                    v = __funnelshift_r(lo, hi, kmis * 8);
-                    const uint32_t rem = n - 4 * i;  // bytes of this word inside the chunk
-                    if (rem < 4) v &= (1u << (8 * rem)) - 1;
-                }
-                s_data32[i] = v;
-            }
-            for (uint32_t i = t; i < NBUCKET / 2 + 4; i += T) s_cnt32[i] = 0;
-            for (uint32_t i = t; i < 288; i += T) sm->hist_lit[i] = 0;
-            if (t < 32) sm->hist_dist[t] = 0;
-            for (uint32_t i = t; i < 160; i += T) reinterpret_cast<uint32_t*>(sm->hdr)[i] = 0;
-        }
-        __syncthreads();
-        PROF(0)
-        const uint32_t nh = n >= 4 ? n - 3 : 0;  // hashed positions
-
-        // ---- Adler-32 of the chunk (parallel partial sums, n <= 32768) --------------------
-        {
-            uint32_t sa = 0, sb = 0;
-            for (uint32_t p = t; p < n; p += T) {
-                uint32_t b = s_data[p];
-                sa += b;
-                sb += (n - p) * b;  // <= 32768*255 per term, <= 128 terms per thread at T>=256
-                if (sb >= 0x80000000u) sb %= 65521u;
-            }
-            sb %= 65521u;
-            uint32_t tot_a, tot_b;
-            block_excl_scan(sa, sm->warp_tmp, &tot_a);
-            block_excl_scan(sb, sm->warp_tmp, &tot_b);
-            if (t == 0) {
-                sm->adler_a = (1u + tot_a) % 65521u;
-                sm->adler_b = (n % 65521u + tot_b) % 65521u;
-            }
-        }
-
-        PROF(1)
-        const bool stored_only = a.level == 0;
-        if (!stored_only) {
-            // ---- P1: hash histogram --------------------------------------------------------
-            for (uint32_t p = t; p < nh; p += T) {
-                const uint32_t h = hash4(ld32u(s_data32, p));
-                atomicAdd(&s_cnt32[h >> 1], 1u << (16 * (h & 1)));
-            }
-            __syncthreads();
-            PROF(2)
-            // ---- P2: inclusive scan over buckets -> bucket ends ------------------------------
-            {
-                const uint32_t per = NBUCKET / T;  // buckets per thread (T divides NBUCKET)
-                uint32_t sum = 0;
-                for (uint32_t i = 0; i < per; i++) sum += s_cnt16[t * per + i];
-                uint32_t tot;
-                uint32_t run = block_excl_scan(sum, sm->warp_tmp, &tot);
-                for (uint32_t i = 0; i < per; i++) {
-                    run += s_cnt16[t * per + i];
-                    s_cnt16[t * per + i] = (uint16_t)run;
-                }
-                if (t == 0) s_cnt16[NBUCKET] = (uint16_t)nh;
-            }
-            __syncthreads();
-            PROF(3)
-            // ---- P3: scatter (ends count down to starts) ------------------------------------
-            for (uint32_t p = t; p < nh; p += T) {
-                const uint32_t h = hash4(ld32u(s_data32, p));
-                const uint32_t sh = 16 * (h & 1);
-                const uint32_t old = atomicSub(&s_cnt32[h >> 1], 1u << sh);
-                s_sorted[((old >> sh) & 0xffffu) - 1] = (uint16_t)p;
-            }
-            __syncthreads();
-            PROF(4)
-            // ---- P4: best match of every position -------------------------------------------
-            for (uint32_t p = t; p < n; p += T) {
-                uint32_t best = 3, bdist = 0;
-                if (p < nh) {
-                    const uint32_t v = ld32u(s_data32, p);
-                    const uint32_t h = hash4(v);
-                    const uint32_t maxl = n - p < (uint32_t)MAX_MATCH ? n - p : (uint32_t)MAX_MATCH;
-                    const uint32_t b0 = s_cnt16[h], b1 = s_cnt16[h + 1];
-                    int ex = 0;
-                    for (uint32_t i = b0; i < b1 && ex < OWN_CAP; i++) {
-                        const uint32_t q = s_sorted[i];
-                        if (q >= p) continue;
-                        ex++;
-                        if (ld32u(s_data32, q) != v) continue;
-                        uint32_t l = 4;
-                        while (l < maxl) {
-                            const uint32_t x = ld32u(s_data32, p + l) ^ ld32u(s_data32, q + l);
-                            if (x) {
-                                l += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                                break;
-                            }
-                            l += 4;
-                        }
-                        if (l > maxl) l = maxl;
-                        const uint32_t dist = p - q;
-                        if (l > best || (l == best && dist < bdist)) {
-                            best = l;
-                            bdist = dist;
-                        }
-                        if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
-                    }
-                    if (a.dict_len && best < (uint32_t)NICE_LENGTH && best < maxl) {
-                        const uint32_t d0 = __ldg(&a.dict->boff[h]), d1 = __ldg(&a.dict->boff[h + 1]);
-                        int exd = 0;
-                        for (uint32_t i = d0; i < d1 && exd < DICT_CAP; i++, exd++) {
-                            if (__ldg(&a.dict->first4[i]) != v) continue;
-                            const uint32_t jpos = __ldg(&a.dict->sorted[i]);
-                            const uint32_t dist = p + a.dict_len - jpos;
-                            if (dist > (uint32_t)WSIZE) continue;
-                            uint32_t lim = a.dict_len - jpos;  // matches do not run from the dictionary into the chunk
-                            if (lim > maxl) lim = maxl;
-                            uint32_t l = 4;
-                            while (l < lim) {
-                                const uint32_t x = ld32u(s_data32, p + l) ^ ldg32u(a.dict->bytes, jpos + l);
-                                if (x) {
-                                    l += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                                    break;
-                                }
-                                l += 4;
-                            }
-                            if (l > lim) l = lim;
-                            if (l > best) {  // equal length: the own-chunk match is nearer
-                                best = l;
-                                bdist = dist;
-                            }
-                            if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
-                        }
-                    }
-                }
-                g_match[p] = best >= 4 ? (best << 16) | (bdist - 1) : 0u;
-            }
-            __syncthreads();
-            PROF(5)
-        }
-
-        // ranges of 32 positions, blocked over threads
-        const uint32_t R = (n + 31) >> 5;
-        const uint32_t rpt = (R + T - 1) / T;
-        const uint32_t r0 = t * rpt, r1 = (r0 + rpt < R) ? r0 + rpt : R;
-
-        if (!stored_only) {
-            // ---- P5: backward DP: exit[p] = first chain position past p's range -------------
-            for (uint32_t r = r0; r < r1; r++) {
-                const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
-                uint32_t nxt_len = pe < n ? (g_match[pe] >> 16) : 0;
-                for (uint32_t p = pe; p-- > ps;) {
-                    const uint32_t mw = g_match[p];
-                    const uint32_t L = mw >> 16;
-                    const bool lazy_lit = L != 0 && L < (uint32_t)MAX_LAZY && nxt_len > L;
-                    if (lazy_lit) g_match[p] = mw | 0x8000u;
-                    const uint32_t next = (L == 0 || lazy_lit) ? p + 1 : p + L;
-                    s_exit[p] = (uint16_t)(next >= pe ? next : s_exit[next]);
-                    nxt_len = L;
-                }
-            }
-            for (uint32_t r = t; r < R; r += T) s_entry[r] = 0xFF;
-            __syncthreads();
-            PROF(6)
-            // ---- P6: hop the true chain across ranges -----------------------------------------
-            if (t == 0) {
-                uint32_t p = 0;
-                while (p < n) {
-                    s_entry[p >> 5] = (uint8_t)(p & 31);
-                    p = s_exit[p];
-                }
-            }
-            __syncthreads();
-            PROF(7)
-            // ---- P7: symbol histograms ----------------------------------------------------------
-            for (uint32_t r = r0; r < r1; r++) {
-                const uint32_t e = s_entry[r];
-                if (e == 0xFF) continue;
-                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
-                for (uint32_t p = (r << 5) + e; p < pe;) {
-                    const Tok tk = token_at(g_match[p], s_data[p]);
-                    atomicAdd(&sm->hist_lit[tk.lsym], 1u);
-                    if (tk.is_match) atomicAdd(&sm->hist_dist[tk.dsym], 1u);
-                    p += tk.step;
-                }
-            }
-            if (t == 0) atomicAdd(&sm->hist_lit[EOB], 1u);
-            __syncthreads();
-            PROF(8)
-            // ---- P8: Huffman codes + header -------------------------------------------------------
-            // parallel rank sort of the literal/length alphabet by (freq, symbol)
-            if (t == 0) {
-                uint32_t used = 0;
-                for (int s = 0; s < NLIT; s++) used += sm->hist_lit[s] != 0;
-                if (used < 2) sm->hist_lit[sm->hist_lit[0] ? 1 : 0] = 1;  // EOB is always used: force a second code
-                sm->n_used = used < 2 ? 2 : used;
-            }
-            __syncthreads();
-            for (uint32_t s = t; s < (uint32_t)NLIT; s += T) {
-                const uint32_t f = sm->hist_lit[s];
-                if (f) {
-                    uint32_t rank = 0;
-                    for (uint32_t o = 0; o < (uint32_t)NLIT; o++) {
-                        const uint32_t g = sm->hist_lit[o];
-                        rank += (g != 0) && (g < f || (g == f && o < s));
-                    }
-                    hw->w[rank] = f;
-                    hw->order[rank] = (uint16_t)s;
-                }
-            }
-            __syncthreads();
-            if (t == 0) {
-                build_lengths_sorted(*hw, (int)sm->n_used, 15, dh->lit_lens, NLIT);
-                uint32_t df[32];
-                for (int s = 0; s < 32; s++) df[s] = sm->hist_dist[s];
-                build_lengths(df, NDIST, 15, dh->dist_lens, *hw);
-                plan_header_from_lengths(*dh, *hw);
-                uint64_t dyn_bits = dh->bits, fix_bits = 3;
-                for (int s = 0; s < NLIT; s++) {
-                    const uint32_t f = sm->hist_lit[s];
-                    const int xb = s > 256 ? lsym_extra(s) : 0;
-                    dyn_bits += (uint64_t)f * (dh->lit_lens[s] + xb);
-                    fix_bits += (uint64_t)f * (fixed_lit_len(s) + xb);
-                }
-                for (int s = 0; s < NDIST; s++) {
-                    dyn_bits += (uint64_t)sm->hist_dist[s] * (dh->dist_lens[s] + dsym_extra(s));
-                    fix_bits += (uint64_t)sm->hist_dist[s] * (5 + dsym_extra(s));
-                }
-                // a forced second literal code has frequency 1 but is never emitted: the estimate is
-                // an upper bound by <= 15 bits, the emitted size below is exact
-                uint32_t mode = dyn_bits < fix_bits ? 2u : 1u;
-                const uint64_t best_bits = dyn_bits < fix_bits ? dyn_bits : fix_bits;
-                if ((uint64_t)n + 5 <= (best_bits + 7) / 8) mode = 0;
-                sm->mode = mode;
-                BitWriter bw{sm->hdr, 0};
-                if (mode == 2) {
-                    write_dynamic_header(*dh, bw, 1);
-                    assign_codes(dh->lit_lens, NLIT, sm->code_lit);
-                    assign_codes(dh->dist_lens, NDIST, sm->code_dist);
-                } else if (mode == 1) {
-                    bw.put(1, 1);
-                    bw.put(1, 2);
-                    for (int s = 0; s < 288; s++) dh->lit_lens[s] = (uint8_t)fixed_lit_len(s);
-                    for (int s = 0; s < 32; s++) dh->dist_lens[s] = 5;
-                    assign_codes(dh->lit_lens, 288, sm->code_lit);
-                    assign_codes(dh->dist_lens, NDIST, sm->code_dist);
-                }
-                sm->hdr_bits = (uint32_t)bw.bitpos;
-            }
-            __syncthreads();
-        } else if (t == 0) {
-            sm->mode = 0;
-        }
-        __syncthreads();
-        const uint32_t mode = sm->mode;
-        PROF(9)
-
+        const uint32_t n = rec.n;
         uint32_t stream_len;
-        if (mode != 0) {
-            // ---- P9: bits per thread, block scan --------------------------------------------------
+        if (rec.mode != 0) {
+            for (uint32_t i = t; i < REC_WORDS; i += T) s_codes[i] = a.hist[(size_t)bj * REC_WORDS + i];
+            const uint32_t hbytes = (rec.hdr_bits + 7) >> 3;
+            for (uint32_t i = t; i < 160; i += T) s_hdr[i] = 0;
+            __syncthreads();
+            {
+                const uint8_t* gh = a.hdrs + (size_t)bj * 640;
+                uint8_t* sh = reinterpret_cast<uint8_t*>(s_hdr);
+                for (uint32_t i = t; i < hbytes; i += T) sh[i] = gh[i];
+            }
+            const uint16_t* tk = a.tokens + (size_t)bj * a.nmax;
+            const uint32_t W = rec.n_words;
+            const uint32_t per = (W + T - 1) / T;
+            const uint32_t w0 = t * per < W ? t * per : W, w1 = w0 + per < W ? w0 + per : W;
             uint32_t bits = 0;
-            for (uint32_t r = r0; r < r1; r++) {
-                const uint32_t e = s_entry[r];
-                if (e == 0xFF) continue;
-                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
-                for (uint32_t p = (r << 5) + e; p < pe;) {
-                    const Tok tk = token_at(g_match[p], s_data[p]);
-                    bits += sm->code_lit[tk.lsym] >> 16;
-                    if (tk.is_match) bits += tk.lbits + (sm->code_dist[tk.dsym] >> 16) + tk.dbits;
-                    p += tk.step;
+            {
+                uint32_t prev = w0 ? tk[w0 - 1] : 0u;
+                if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;  // prev is itself a distance word
+                for (uint32_t i = w0; i < w1; i++) {
+                    const uint32_t w = tk[i];
+                    uint32_t val, nb;
+                    word_bits(s_codes, w, prev, val, nb);
+                    bits += nb;
+                    prev = (prev & 0x8000u) ? 0u : w;  // a distance word never introduces another one
                 }
             }
             uint32_t tok_bits;
-            const uint32_t my_off = sm->hdr_bits + block_excl_scan(bits, sm->warp_tmp, &tok_bits);
-            const uint32_t eob = sm->code_lit[EOB];
-            const uint32_t total_bits = sm->hdr_bits + tok_bits + (eob >> 16);
+            const uint32_t my_off = rec.hdr_bits + block_excl_scan(bits, s_tmp, &tok_bits);
+            const uint32_t eob = s_codes[EOB];
+            const uint32_t total_bits = rec.hdr_bits + tok_bits + (eob >> 16);
             const uint32_t body = (total_bits + 7) >> 3;
             stream_len = hdr_len + body + 4;
             // zero the deflate words (+ trailer spill) so shared boundary words can be OR-ed
             const uint32_t zw = (body + 4 + 3) >> 2;
             for (uint32_t i = t; i < zw; i += T) out32[i] = 0;
             __syncthreads();
-            PROF(10)
-            // ---- P10: emission ------------------------------------------------------------------------
             if (t == 0) {  // header bits: whole words stored, last partial word OR-ed
-                const uint32_t hb = sm->hdr_bits;
-                const uint32_t* hwrd = reinterpret_cast<const uint32_t*>(sm->hdr);
-                for (uint32_t i = 0; i < (hb >> 5); i++) out32[i] = hwrd[i];
-                if (hb & 31) atomicOr(out32 + (hb >> 5), hwrd[hb >> 5]);
+                const uint32_t hb = rec.hdr_bits;
+                for (uint32_t i = 0; i < (hb >> 5); i++) out32[i] = s_hdr[i];
+                if (hb & 31) atomicOr(out32 + (hb >> 5), s_hdr[hb >> 5]);
             }
             Emitter em;
             em.begin(out32, my_off);
-            for (uint32_t r = r0; r < r1; r++) {
-                const uint32_t e = s_entry[r];
-                if (e == 0xFF) continue;
-                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
-                for (uint32_t p = (r << 5) + e; p < pe;) {
-                    const Tok tk = token_at(g_match[p], s_data[p]);
-                    const uint32_t lc = sm->code_lit[tk.lsym];
-                    em.put(lc & 0xffffu, lc >> 16);
-                    if (tk.is_match) {
-                        if (tk.lbits) em.put(tk.lval, tk.lbits);
-                        const uint32_t dc = sm->code_dist[tk.dsym];
-                        em.put(dc & 0xffffu, dc >> 16);
-                        if (tk.dbits) em.put(tk.dval, tk.dbits);
-                    }
-                    p += tk.step;
+            {
+                uint32_t prev = w0 ? tk[w0 - 1] : 0u;
+                if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;
+                for (uint32_t i = w0; i < w1; i++) {
+                    const uint32_t w = tk[i];
+                    uint32_t val, nb;
+                    word_bits(s_codes, w, prev, val, nb);
+                    em.put(val, nb);
+                    prev = (prev & 0x8000u) ? 0u : w;
                 }
             }
             em.end();
-            if (t == T - 1) {  // the last thread's range list ends the stream: EOB follows all tokens
+            if (t == T - 1) {  // EOB follows all tokens
                 Emitter ee;
-                ee.begin(out32, sm->hdr_bits + tok_bits);
+                ee.begin(out32, rec.hdr_bits + tok_bits);
                 ee.put(eob & 0xffffu, eob >> 16);
                 ee.end();
             }
             __syncthreads();
             if (t == 0) {
                 uint8_t* tr = slot + 2 + hdr_len + body;
-                const uint32_t ad = (sm->adler_b << 16) | sm->adler_a;
-                tr[0] = (uint8_t)(ad >> 24);
-                tr[1] = (uint8_t)(ad >> 16);
-                tr[2] = (uint8_t)(ad >> 8);
-                tr[3] = (uint8_t)ad;
+                tr[0] = (uint8_t)(rec.adler >> 24);
+                tr[1] = (uint8_t)(rec.adler >> 16);
+                tr[2] = (uint8_t)(rec.adler >> 8);
+                tr[3] = (uint8_t)rec.adler;
             }
         } else {
-            // ---- stored block(s): n <= 32768 -> a single block ---------------------------------------
+            // ---- stored block: n <= 32768 -> a single block ---------------------------------------
+            const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
+            const uint8_t* src = a.data + (j ? a.cuts[j - 1] : a.start0);
             uint8_t* o = slot + 2 + hdr_len;
             if (t == 0) {
                 o[0] = 1;
@@ -538,14 +877,13 @@ __global__ void __launch_bounds__(T_LARGE) deflate_kernel(DeflArgs a) {
                 o[2] = (uint8_t)(n >> 8);
                 o[3] = (uint8_t)~n;
                 o[4] = (uint8_t)(~n >> 8);
-                const uint32_t ad = (sm->adler_b << 16) | sm->adler_a;
                 uint8_t* tr = o + 5 + n;
-                tr[0] = (uint8_t)(ad >> 24);
-                tr[1] = (uint8_t)(ad >> 16);
-                tr[2] = (uint8_t)(ad >> 8);
-                tr[3] = (uint8_t)ad;
+                tr[0] = (uint8_t)(rec.adler >> 24);
+                tr[1] = (uint8_t)(rec.adler >> 16);
+                tr[2] = (uint8_t)(rec.adler >> 8);
+                tr[3] = (uint8_t)rec.adler;
             }
-            for (uint32_t p = t; p < n; p += T) o[5 + p] = s_data[p];
+            for (uint32_t p = t; p < n; p += T) o[5 + p] = src[p];
             stream_len = hdr_len + 5 + n + 4;
         }
         if (t == 0) {
@@ -561,15 +899,13 @@ __global__ void __launch_bounds__(T_LARGE) deflate_kernel(DeflArgs a) {
             }
             a.sizes[k] = stream_len;
         }
-        PROF(11)
-        if (t == 0) atomicAdd(&g_prof[15], 1ull);
     }
 }
 
-// ---- helpers around the main kernel ---------------------------------------------------------
+// ---- helpers around the main kernels -------------------------------------------------------------
 
 // Per selected chunk: worst-case slot size and size class list.  class 0: <= NMAX_SMALL,
-// class 1: <= NMAX_LARGE, class 2: longer (multi-block path).
+// class 1: <= NMAX_LARGE, class 2: longer (multi-block stored path).
 __global__ void classify_kernel(uint64_t start0, const uint64_t* __restrict__ cuts, const uint64_t* __restrict__ select,
                                 uint64_t m, uint64_t* __restrict__ slot_size, uint32_t* __restrict__ lists,
                                 uint32_t* __restrict__ list_n) {
@@ -589,8 +925,7 @@ __global__ void classify_kernel(uint64_t start0, const uint64_t* __restrict__ cu
 __global__ void __launch_bounds__(256)
 stored_kernel(DeflArgs a) {
     __shared__ uint32_t s_a[256], s_b[256];
-    const uint32_t list_n = *a.list_n;
-    for (uint32_t job = blockIdx.x; job < list_n; job += gridDim.x) {
+    for (uint32_t job = a.job0 + blockIdx.x; job < a.job1; job += gridDim.x) {
         const uint32_t k = a.list[job];
         const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
         const uint64_t cs = j ? a.cuts[j - 1] : a.start0;
@@ -599,8 +934,7 @@ stored_kernel(DeflArgs a) {
         uint8_t* slot = a.stage + a.slot_off[k];
         const uint32_t hdr_len = a.dict_len ? 6 : 2;
         uint8_t* o = slot + 2 + hdr_len;
-        const uint64_t nblk = n / 65535 + 1;  // the last block may be empty-length only when n % 65535 == 0
-        // Adler-32 in segments of 256 bytes per thread-step
+        const uint64_t nblk = n / 65535 + 1;  // the last block may have length 0 only when n % 65535 == 0
         uint64_t sa = 0, sb = 0;
         for (uint64_t p = threadIdx.x; p < n; p += 256) {
             const uint64_t b = src[p];
@@ -693,6 +1027,7 @@ struct DictHost {
     uint32_t adler;
     int valid;
 };
+
 int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32_t* adler, cudaStream_t st) {
     HMSE_SCRATCH(ctx, dev, DictDev*, SLOT_DEFLATE_DICT, sizeof(DictDev));
     DictHost* hd = (DictHost*)ctx->dict_host;
@@ -727,8 +1062,13 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
     for (uint32_t j = nh; j-- > 0;) {
         const uint32_t v = le32(j), h = hash4(v);
         const uint32_t i = cnt[h]++;
-        img->sorted[i] = (uint16_t)j;
-        img->first4[i] = v;
+        img->ent[i].first4 = v;
+        uint32_t nx = 0;
+        for (uint32_t b = 0; b < 4; b++)
+            if (j + 4 + b < dict_len) nx |= (uint32_t)tmp[j + 4 + b] << (8 * b);
+        img->ent[i].next4 = nx;
+        img->ent[i].pos = j;
+        img->ent[i].pad = 0;
     }
     free(cnt);
     cudaError_t e = cudaMemcpyAsync(dev, img, sizeof(DictDev), cudaMemcpyHostToDevice, st);
@@ -740,8 +1080,9 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
     return HMSE_OK;
 }
 
-size_t smem_for(uint32_t nmax) {
-    return (size_t)nmax + 16 + 2 * (size_t)nmax + (NBUCKET / 2 + 4) * 4 + nmax / 32 + sizeof(Small) + 64;
+size_t parse_smem(uint32_t nmax, bool match_smem) {
+    return (size_t)nmax + 16 + 2 * (size_t)(nmax + nmax / 32) + CNT_WORDS * 4 + nmax / 32 + NBUCKET / 8 +
+           ((sizeof(ParseSm) + 15) & ~15u) + (match_smem ? 4 * (size_t)(nmax + nmax / 32) : (size_t)nmax) + 64;
 }
 
 }  // namespace
@@ -780,18 +1121,18 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         int rc = ensure_dict(ctx, d_zdict, dict_len, &dict_adler, st);
         if (rc) return rc;
     }
-    // misc: [slot_size m][slot_off m][sizes m+1][lists 3m u32][list_n 4 u32][counters 4 u32][total u64]
-    const size_t misc_bytes = (3 * m + 2) * 8 + 3 * m * 4 + 64;
+    // misc: [slot_size m][slot_off m][sizes m+1][lists 3m u32][list_n 4 u32][totals][counters]
+    const size_t n_counters = 2 * (m / (BATCH_LARGE < BATCH_SMALL ? BATCH_LARGE : BATCH_SMALL) + 2);
+    const size_t misc_bytes = (3 * m + 2) * 8 + 3 * m * 4 + 64 + n_counters * 4 + 64;
     HMSE_SCRATCH(ctx, misc, uint8_t*, SLOT_DEFLATE_MISC, misc_bytes);
     uint64_t* slot_size = (uint64_t*)misc;
     uint64_t* slot_off = slot_size + m;
     uint64_t* sizes = slot_off + m;  // m + 1
     uint32_t* lists = (uint32_t*)(sizes + m + 1);
     uint32_t* list_n = lists + 3 * m;
-    unsigned int* counters = list_n + 4;
-    uint64_t* d_tot = (uint64_t*)(counters + 4);  // [stage total, out total]
-    d_tot = (uint64_t*)(((uintptr_t)d_tot + 7) & ~(uintptr_t)7);
-    HMSE_CUDA(ctx, cudaMemsetAsync(list_n, 0, 64, st));
+    uint64_t* d_tot = (uint64_t*)(((uintptr_t)(list_n + 4) + 7) & ~(uintptr_t)7);  // [stage total, out total]
+    unsigned int* counters = (unsigned int*)(d_tot + 2);
+    HMSE_CUDA(ctx, cudaMemsetAsync(list_n, 0, 48 + n_counters * 4, st));
     KL(ctx);
     classify_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(start0, d_cuts, d_select, m, slot_size, lists, list_n);
     HMSE_LAUNCH_CHECK(ctx);
@@ -803,10 +1144,11 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t stage_bytes = mail[0];
     const uint32_t* hn = (const uint32_t*)(mail + 1);
-    const uint32_t n_small = hn[0], n_large = hn[1], n_huge = hn[2];
+    const uint32_t n_class[3] = {hn[0], hn[1], hn[2]};
     HMSE_SCRATCH(ctx, stage, uint8_t*, SLOT_DEFLATE_STAGE, stage_bytes + 64);
 
     DeflArgs a;
+    memset(&a, 0, sizeof(a));
     a.data = d_data;
     a.start0 = start0;
     a.cuts = d_cuts;
@@ -819,39 +1161,63 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     a.slot_off = slot_off;
     a.sizes = sizes;
 
-    const size_t sm_small = smem_for(NMAX_SMALL), sm_large = smem_for(NMAX_LARGE);
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_large));
-    const uint32_t max_small = (uint32_t)ctx->sm_count * 3, max_large = (uint32_t)ctx->sm_count;
-    const uint32_t g_small = n_small < max_small ? n_small : max_small;
-    const uint32_t g_large = n_large < max_large ? n_large : max_large;
-    HMSE_SCRATCH(ctx, work, uint32_t*, SLOT_DEFLATE_WORK,
-                 ((size_t)g_small * NMAX_SMALL + (size_t)g_large * NMAX_LARGE) * 4 + 64);
+    const size_t sm_parse[2] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_LARGE, false)};
+    const size_t sm_huff = sizeof(HuffSm) * HUFF_WARPS;
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sm_parse[0] > sm_parse[1] ? sm_parse[0] : sm_parse[1])));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_huff));
+    const uint32_t nmax_c[2] = {NMAX_SMALL, NMAX_LARGE};
+    const uint32_t batch_c[2] = {BATCH_SMALL, BATCH_LARGE};
+    const uint32_t ctas_c[2] = {(uint32_t)ctx->sm_count * 2, (uint32_t)ctx->sm_count};
+    // work scratch: tokens (u16 per input byte, per batch job), hist/codes, headers, records, large-class match
+    size_t tok_bytes = 0, rec_jobs = 1;
+    for (int c = 0; c < 2; c++) {
+        const uint32_t jobs = n_class[c] < batch_c[c] ? n_class[c] : batch_c[c];
+        if ((size_t)jobs * nmax_c[c] * 2 > tok_bytes) tok_bytes = (size_t)jobs * nmax_c[c] * 2;
+        if (jobs > rec_jobs) rec_jobs = jobs;
+    }
+    tok_bytes = (tok_bytes + 255) & ~(size_t)255;
+    const uint32_t g_large = n_class[1] < ctas_c[1] ? n_class[1] : ctas_c[1];
+    const size_t work_bytes = tok_bytes + rec_jobs * (REC_WORDS * 4 + 640 + sizeof(ChunkRec)) +
+                              (size_t)g_large * (NMAX_LARGE + NMAX_LARGE / 32) * 4 + 1024;
+    HMSE_SCRATCH(ctx, work, uint8_t*, SLOT_DEFLATE_WORK, work_bytes);
+    a.tokens = (uint16_t*)work;
+    a.hist = (uint32_t*)(work + tok_bytes);
+    a.hdrs = (uint8_t*)(a.hist + rec_jobs * REC_WORDS);
+    a.recs = (ChunkRec*)(a.hdrs + rec_jobs * 640);
+    a.match = (uint32_t*)(a.recs + rec_jobs);
+
     HT_BEGIN(ctx, HT_DEFLATE, st);
-    if (g_small) {
-        a.list = lists;
-        a.list_n = list_n;
-        a.nmax = NMAX_SMALL;
-        a.match = work;
-        a.counter = counters;
-        KL(ctx);
-        deflate_kernel<<<g_small, T_SMALL, sm_small, st>>>(a);
-        HMSE_LAUNCH_CHECK(ctx);
+    uint32_t ci = 0;
+    for (int c = 0; c < 2; c++) {
+        a.list = lists + (size_t)c * m;
+        a.nmax = nmax_c[c];
+        a.match_smem = c == 0;
+        for (uint32_t j0 = 0; j0 < n_class[c]; j0 += batch_c[c]) {
+            a.job0 = j0;
+            a.job1 = j0 + batch_c[c] < n_class[c] ? j0 + batch_c[c] : n_class[c];
+            a.counter = counters + ci++;
+            const uint32_t jobs = a.job1 - a.job0;
+            KL(ctx);
+            parse_kernel<<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            if (level != 0) {
+                const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
+                const uint32_t hmax = (uint32_t)ctx->sm_count * 3;
+                KL(ctx);
+                huffman_kernel<<<hb < hmax ? hb : hmax, HUFF_WARPS * 32, sm_huff, st>>>(a);
+            }
+            const uint32_t emax = (uint32_t)ctx->sm_count * 8;
+            KL(ctx);
+            encode_kernel<<<jobs < emax ? jobs : emax, T_ENCODE, 0, st>>>(a);
+            HMSE_LAUNCH_CHECK(ctx);
+        }
     }
-    if (g_large) {
-        a.list = lists + m;
-        a.list_n = list_n + 1;
-        a.nmax = NMAX_LARGE;
-        a.match = work + (size_t)g_small * NMAX_SMALL;
-        a.counter = counters + 1;
-        KL(ctx);
-        deflate_kernel<<<g_large, T_LARGE, sm_large, st>>>(a);
-        HMSE_LAUNCH_CHECK(ctx);
-    }
-    if (n_huge) {
+    if (n_class[2]) {
         a.list = lists + 2 * m;
-        a.list_n = list_n + 2;
+        a.job0 = 0;
+        a.job1 = n_class[2];
         KL(ctx);
-        stored_kernel<<<n_huge < 1024 ? n_huge : 1024, 256, 0, st>>>(a);
+        stored_kernel<<<n_class[2] < 1024 ? n_class[2] : 1024, 256, 0, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
     }
     HT_END(ctx, HT_DEFLATE, st);

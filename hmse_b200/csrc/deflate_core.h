@@ -85,33 +85,52 @@ DFL_HD uint32_t bitrev(uint32_t code, int len) {
     return r;
 }
 
-// Sequential bit writer into a byte buffer that is zero-initialised (LSB-first, RFC 1951).
+// Sequential LSB-first bit writer (RFC 1951 packing) into a byte buffer; starts byte aligned.
+// finish() flushes the last partial byte; bitpos is the number of bits written.
 struct BitWriter {
     uint8_t* buf;
     uint64_t bitpos;
+    uint64_t acc = 0;
+    int nacc = 0;
     DFL_HD void put(uint32_t value, int nbits) {
-        for (int i = 0; i < nbits; i++) {
-            if ((value >> i) & 1) buf[bitpos >> 3] |= (uint8_t)(1u << (bitpos & 7));
-            bitpos++;
+        acc |= (uint64_t)value << nacc;
+        nacc += nbits;
+        while (nacc >= 8) {
+            buf[bitpos >> 3] = (uint8_t)acc;
+            acc >>= 8;
+            nacc -= 8;
+            bitpos += 8;
+        }
+    }
+    DFL_HD void finish() {
+        if (nacc) {
+            buf[bitpos >> 3] = (uint8_t)acc;
+            bitpos += (uint64_t)nacc;
+            nacc = 0;
+            acc = 0;
         }
     }
 };
 
-// Scratch for one Huffman construction (n <= 288 symbols).
-struct HuffWork {
-    uint32_t w[2 * 288];      // node weights: leaves (sorted ascending) then internal nodes
-    uint16_t parent[2 * 288];
-    uint16_t order[288];      // leaf i (sorted position) -> symbol
-    uint16_t bl_count[17];
+// Scratch for one Huffman construction over at most CAP symbols.
+template <int CAP>
+struct HuffWorkT {
+    uint32_t w[2 * CAP];      // node weights: leaves (sorted ascending) then internal nodes
+    uint16_t parent[2 * CAP];
+    uint16_t order[CAP];      // leaf i (sorted position) -> symbol
+    uint16_t bl_count[18];
 };
+using HuffWork = HuffWorkT<288>;
+using HuffWorkSmall = HuffWorkT<32>;
 
 // Length-limited Huffman code lengths from k >= 2 leaves already sorted ascending by
 // (freq, symbol) in hw.w[0..k) / hw.order[0..k).  lens[0..n) receives 0 for unused symbols.
 // Depth overflow is repaired with the bl_count move zlib's gen_bitlen uses, so the code is
 // always complete (inflate rejects incomplete sets).
-DFL_HD void build_lengths_sorted(HuffWork& hw, int k, int maxbits, uint8_t* lens, int n) {
-    for (int s = 0; s < n; s++) lens[s] = 0;
-    // two-queue merge: leaves 0..k-1 ascending, internal nodes k..2k-2 are created ascending
+// Two-queue Huffman merge over k sorted leaves: leaves 0..k-1, internal nodes k..2k-2 (created in
+// ascending weight order, so parents always have larger indices); root = 2k-2.
+template <class HW>
+DFL_HD void huff_merge(HW& hw, int k) {
     int leaf = 0, inode = k, next = k;
     for (int i = 0; i < k - 1; i++) {
         int a, b;
@@ -122,8 +141,27 @@ DFL_HD void build_lengths_sorted(HuffWork& hw, int k, int maxbits, uint8_t* lens
         hw.parent[b] = (uint16_t)next;
         next++;
     }
+}
+
+// zlib gen_bitlen's overflow repair on a per-length leaf histogram whose Kraft sum (in units of
+// 2^-maxbits) is `kraft`: afterwards the histogram describes a complete prefix code.
+DFL_HD void huff_fix_overflow(uint16_t* bl_count, int maxbits, uint64_t kraft) {
+    while (kraft > (1ull << maxbits)) {
+        int bits = maxbits - 1;
+        while (bl_count[bits] == 0) bits--;
+        bl_count[bits]--;
+        bl_count[bits + 1] += 2;
+        bl_count[maxbits]--;
+        kraft--;
+    }
+}
+
+template <class HW>
+DFL_HD void build_lengths_sorted(HW& hw, int k, int maxbits, uint8_t* lens, int n) {
+    for (int s = 0; s < n; s++) lens[s] = 0;
+    huff_merge(hw, k);
     const int root = 2 * k - 2;
-    // depths: parents have larger indices than their children; w[] of internal nodes becomes depth
+    // depths: w[] of internal nodes becomes depth
     hw.w[root] = 0;
     for (int i = root - 1; i >= k; i--) hw.w[i] = hw.w[hw.parent[i]] + 1;
     for (int b = 0; b <= maxbits; b++) hw.bl_count[b] = 0;
@@ -134,14 +172,7 @@ DFL_HD void build_lengths_sorted(HuffWork& hw, int k, int maxbits, uint8_t* lens
         hw.bl_count[d]++;
         kraft += 1ull << (maxbits - d);
     }
-    while (kraft > (1ull << maxbits)) {
-        int bits = maxbits - 1;
-        while (hw.bl_count[bits] == 0) bits--;
-        hw.bl_count[bits]--;
-        hw.bl_count[bits + 1] += 2;
-        hw.bl_count[maxbits]--;
-        kraft--;
-    }
+    huff_fix_overflow(hw.bl_count, maxbits, kraft);
     // rarest symbols take the longest codes
     int i = 0;
     for (int bits = maxbits; bits >= 1; bits--)
@@ -150,7 +181,8 @@ DFL_HD void build_lengths_sorted(HuffWork& hw, int k, int maxbits, uint8_t* lens
 
 // Same from raw frequencies: forces at least two codes (zlib trees.c build_tree does the same)
 // and insertion-sorts the used symbols by (freq, symbol).  freq[] may be modified.
-DFL_HD void build_lengths(uint32_t* freq, int n, int maxbits, uint8_t* lens, HuffWork& hw) {
+template <class HW>
+DFL_HD void build_lengths(uint32_t* freq, int n, int maxbits, uint8_t* lens, HW& hw) {
     int k = 0;
     for (int s = 0; s < n; s++)
         if (freq[s]) k++;
@@ -251,7 +283,8 @@ struct DynHeader {
 
 // Header plan from finished lit/dist code lengths: trims trailing zeros, run-length codes the
 // lengths, builds the code-length code.  Returns the header size in bits incl. BFINAL/BTYPE.
-DFL_HD uint32_t plan_header_from_lengths(DynHeader& h, HuffWork& hw) {
+template <class HW>
+DFL_HD uint32_t plan_header_from_lengths(DynHeader& h, HW& hw) {
     h.nlit = NLIT;
     while (h.nlit > 257 && h.lit_lens[h.nlit - 1] == 0) h.nlit--;
     h.ndist = NDIST;
@@ -297,6 +330,15 @@ DFL_HD void write_dynamic_header(const DynHeader& h, BitWriter& bw, int bfinal) 
         else if (s == 18) bw.put((uint32_t)ev, 7);
     }
 }
+
+// Fixed-Huffman codes (RFC 1951 3.2.6), bit-reversed, packed len<<16 | code.
+DFL_HD uint32_t fixed_lit_code(int s) {
+    if (s < 144) return (8u << 16) | bitrev(0x30u + (uint32_t)s, 8);
+    if (s < 256) return (9u << 16) | bitrev(0x190u + (uint32_t)(s - 144), 9);
+    if (s < 280) return (7u << 16) | bitrev((uint32_t)(s - 256), 7);
+    return (8u << 16) | bitrev(0xC0u + (uint32_t)(s - 280), 8);
+}
+DFL_HD uint32_t fixed_dist_code(int s) { return (5u << 16) | bitrev((uint32_t)s, 5); }
 
 // Fixed-Huffman code lengths (RFC 1951 3.2.6).
 DFL_HD int fixed_lit_len(int s) { return s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8; }

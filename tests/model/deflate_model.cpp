@@ -134,7 +134,9 @@ extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t
         o[1] = n & 0xff; o[2] = n >> 8; o[3] = ~n & 0xff; o[4] = (~n >> 8) & 0xff;
         memcpy(o + 5, data, n);
     } else {
-        BitWriter bw{out + hdr, 0};
+        BitWriter bw;
+        bw.buf = out + hdr;
+        bw.bitpos = 0;
         uint32_t lc[288], dc[32];
         if (mode == 2) {
             write_dynamic_header(h, bw, 1);
@@ -143,11 +145,8 @@ extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t
         } else {
             bw.put(1, 1);
             bw.put(1, 2);
-            uint8_t fl[288], fd[32];
-            for (int s = 0; s < 288; s++) fl[s] = (uint8_t)fixed_lit_len(s);
-            for (int s = 0; s < 32; s++) fd[s] = 5;
-            assign_codes(fl, 288, lc);
-            assign_codes(fd, 30, dc);
+            for (int s = 0; s < 288; s++) lc[s] = fixed_lit_code(s);
+            for (int s = 0; s < 30; s++) dc[s] = fixed_dist_code(s);
         }
         for (uint32_t t : tok) {
             if (!(t >> 31)) {
@@ -163,6 +162,7 @@ extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t
             }
         }
         bw.put(lc[EOB] & 0xffff, lc[EOB] >> 16);
+        bw.finish();
         if ((bw.bitpos + 7) / 8 != body) return -1000000 - (int64_t)bw.bitpos;
     }
     uint32_t a = adler32(data, n);
