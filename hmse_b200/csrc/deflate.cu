@@ -31,7 +31,7 @@ using namespace dfl;
 
 namespace {
 
-constexpr int OWN_CAP = 16;       // nearest own-chunk candidates examined per position
+constexpr int OWN_CAP = 8;        // nearest own-chunk candidates examined per position
 constexpr int DICT_CAP = 8;       // nearest dictionary candidates examined per position (2 batches of 4)
 constexpr uint32_t DICT_MAX = 32768;
 constexpr uint32_t NMAX_SMALL = 12288, NMAX_LARGE = 32768;
@@ -171,39 +171,6 @@ __device__ __forceinline__ uint32_t extend_dict(const uint32_t* d32, const uint8
     return l > lim ? lim : l;
 }
 
-// Ascending bitonic sort of a[0..k) by one warp ("normalised" network: every compare-exchange
-// is ascending, so virtual +inf padding past k never moves).
-__device__ __forceinline__ void warp_sort_u16(uint16_t* a, uint32_t k, unsigned lane) {
-    uint32_t P = 2;
-    while (P < k) P <<= 1;
-    for (uint32_t size = 2; size <= P; size <<= 1) {
-        for (uint32_t i = lane; i < P; i += 32) {
-            const uint32_t l = i ^ (size - 1);
-            if (l > i && l < k) {
-                const uint16_t x = a[i], y = a[l];
-                if (x > y) {
-                    a[i] = y;
-                    a[l] = x;
-                }
-            }
-        }
-        __syncwarp();
-        for (uint32_t j = size >> 2; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < P; i += 32) {
-                const uint32_t l = i ^ j;
-                if (l > i && l < k) {
-                    const uint16_t x = a[i], y = a[l];
-                    if (x > y) {
-                        a[i] = y;
-                        a[l] = x;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 // Per-range passes touch element 32*r + j from lane r: a skew of one element per 32 makes those
 // accesses conflict free in shared memory.
 __device__ __forceinline__ uint32_t SK(uint32_t p) { return p + (p >> 5); }
@@ -226,13 +193,12 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + nmax + 16 + 2 * (size_t)(nmax + nmax / 32));  // CNT_WORDS
     uint16_t* s_E = reinterpret_cast<uint16_t*>(s_cnt32);  // bucket h = sorted[E[h] .. E[h+1])
     uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CNT_WORDS);         // nmax/32 bytes
-    uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_entry + nmax / 32);        // NBUCKET bits
-    ParseSm* sm = reinterpret_cast<ParseSm*>(s_flag + NBUCKET / 32);
+    uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_entry + nmax / 32);        // nmax bits
+    ParseSm* sm = reinterpret_cast<ParseSm*>(s_flag + nmax / 32);
     uint8_t* s_tail = reinterpret_cast<uint8_t*>(sm) + ((sizeof(ParseSm) + 15) & ~15u);
     // small class: match words in shared memory (skewed); the list of buckets to sort borrows that
     // space before P4.  large class: match words in global scratch, the list has its own space.
     uint32_t* mptr = a.match_smem ? reinterpret_cast<uint32_t*>(s_tail) : a.match + (size_t)blockIdx.x * (nmax + nmax / 32);
-    uint16_t* s_big = reinterpret_cast<uint16_t*>(s_tail);
     uint16_t* s_exit = s_sorted;
 
     for (;;) {
@@ -267,7 +233,6 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             }
             for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;
             for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
-            if (t == 0) sm->n_big = 0;
         }
         __syncthreads();
         PROF(0)
@@ -328,25 +293,33 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 __syncthreads();
             }
             PROF(3)
-            // Buckets are already ordered except for same-hash positions inside one scatter tile.  Every
-            // adjacent pair is checked in parallel; only buckets with an inversion are sorted.
-            for (uint32_t i = t; i < NBUCKET / 32; i += T) s_flag[i] = 0;
+            // Buckets are already ordered except for same-hash positions inside one scatter tile
+            // (common in text: a word repeated within 512 bytes).  Odd-even transposition passes over
+            // all adjacent same-bucket pairs put them in order; groups are tiny, so 2-4 passes do.
+            for (uint32_t i = t; i < (nmax >> 5); i += T) s_flag[i] = 0;   // bit i: sorted index i starts a bucket
             __syncthreads();
-            for (uint32_t i = t + 1; i < nh; i += T) {
-                const uint32_t q0 = s_sorted[i - 1], q1 = s_sorted[i];
-                if (q0 > q1) {
-                    const uint32_t h = hash4(ld32u(s_data32, q1));
-                    if (i > s_E[h]) {  // same bucket: a real inversion
-                        const uint32_t old = atomicOr(&s_flag[h >> 5], 1u << (h & 31));
-                        if (!(old & (1u << (h & 31)))) s_big[atomicAdd(&sm->n_big, 1u)] = (uint16_t)h;
-                    }
-                }
+            for (uint32_t i = 0; i < per; i++) {
+                const uint32_t h = t * per + i;
+                const uint32_t b0 = s_E[h];
+                if (s_E[h + 1] > b0) atomicOr(&s_flag[b0 >> 5], 1u << (b0 & 31));
             }
             __syncthreads();
-            for (uint32_t i = warp; i < sm->n_big; i += nwarps) {
-                const uint32_t h = s_big[i];
-                const uint32_t b0 = s_E[h];
-                warp_sort_u16(s_sorted + b0, (uint32_t)s_E[h + 1] - b0, lane);
+            for (;;) {
+                int changed = 0;
+#pragma unroll
+                for (int parity = 0; parity < 2; parity++) {
+                    for (uint32_t i = 2 * t + parity; i + 1 < nh; i += 2 * T) {
+                        if ((s_flag[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u) continue;  // i+1 starts another bucket
+                        const uint16_t x = s_sorted[i], y = s_sorted[i + 1];
+                        if (x > y) {
+                            s_sorted[i] = y;
+                            s_sorted[i + 1] = x;
+                            changed = 1;
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (!__syncthreads_or(changed)) break;
             }
             __syncthreads();
             PROF(4)
@@ -1081,8 +1054,8 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
 }
 
 size_t parse_smem(uint32_t nmax, bool match_smem) {
-    return (size_t)nmax + 16 + 2 * (size_t)(nmax + nmax / 32) + CNT_WORDS * 4 + nmax / 32 + NBUCKET / 8 +
-           ((sizeof(ParseSm) + 15) & ~15u) + (match_smem ? 4 * (size_t)(nmax + nmax / 32) : (size_t)nmax) + 64;
+    return (size_t)nmax + 16 + 2 * (size_t)(nmax + nmax / 32) + CNT_WORDS * 4 + nmax / 32 + nmax / 8 +
+           ((sizeof(ParseSm) + 15) & ~15u) + (match_smem ? 4 * (size_t)(nmax + nmax / 32) : 0) + 64;
 }
 
 }  // namespace
