@@ -1,0 +1,88 @@
+"""Real multi-GPU check (needs >= 2 CUDA devices): ShardedIngest over NCCL reproduces the
+single-stream cut list, digests and global dedup of the oracle.  Skipped on one-GPU boxes; the
+protocol itself is covered on CPU by tests/test_sharding_gloo.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import hmse_b200
+from hmse_b200 import corpus as pc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+ctx = hmse_b200.Context(rank)
+cfg = hmse_b200.CDCConfig()
+total = 24 << 20
+per = total // world
+gen = pc.DeviceCorpus(ctx)
+eof = rank == world - 1
+n_avail = (total - rank * per) if eof else per + cfg.max_size
+d = gen.generate(n_avail, byte_off=rank * per)
+zd = ctx.stage(pc.zdict())
+res = hmse_b200.ShardedIngest(ctx, cfg, zd).run(d, per, eof)
+torch.cuda.synchronize()
+out = dict(rank=rank, cuts=(res.cuts.cpu().numpy().view(np.uint64) + np.uint64(rank * per)).tolist(),
+           canon=res.canon.cpu().numpy().tolist(), first=res.is_first.cpu().numpy().astype(int).tolist(),
+           digests=res.digests.cpu().numpy().tobytes().hex(), id_base=res.id_base, entry=res.entry,
+           blob=res.blob.cpu().numpy().tobytes().hex(), offs=res.offsets.cpu().numpy().tolist(),
+           sel=res.select.cpu().numpy().tolist())
+json.dump(out, open(os.path.join(%r, "shard_%%d.json" %% rank), "w"))
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_sharded_ingest(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import numpy as np
+    import oracle
+    from oracle import corpus
+    world = 2
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % (ROOT, str(tmp_path)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    outs = [json.load(open(tmp_path / ("shard_%d.json" % k))) for k in range(world)]
+    total = 24 << 20
+    data = corpus.generate(total)
+    want_cuts = oracle.chunk_c(data)
+    cuts = np.array(sum((o["cuts"] for o in outs), []), dtype=np.uint64)
+    assert np.array_equal(cuts, want_cuts)
+    dg = np.frombuffer(bytes.fromhex("".join(o["digests"] for o in outs)), dtype=np.uint8).reshape(-1, 32)
+    want_dg = oracle.digest(data, want_cuts)
+    assert np.array_equal(dg, want_dg)
+    wc, wf = oracle.dedup(want_dg)
+    assert np.array_equal(np.array(sum((o["canon"] for o in outs), []), dtype=np.int64), wc)
+    assert np.array_equal(np.array(sum((o["first"] for o in outs), []), dtype=bool), wf)
+    # every rank compressed exactly its globally-first chunks, and they inflate to the raw bytes
+    zd = corpus.zdict()
+    starts = np.concatenate([[0], want_cuts[:-1]]).astype(np.int64)
+    raw = data.tobytes()
+    for o in outs:
+        blob = np.frombuffer(bytes.fromhex(o["blob"]), dtype=np.uint8)
+        offs = np.array(o["offs"], dtype=np.int64).astype(np.uint64)
+        streams = oracle.inflate_all(blob, offs, zd)
+        assert len(streams) == len(o["sel"])
+        for k, j in enumerate(o["sel"]):
+            g = o["id_base"] + j
+            assert wf[g]
+            assert streams[k] == raw[int(starts[g]):int(want_cuts[g])]
