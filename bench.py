@@ -387,10 +387,20 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # Exactly one line may reach stdout: libraries (NCCL prints its version banner there) are sent
+    # to stderr at the file-descriptor level, and the JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    sys.stdout = real_stdout
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":

@@ -272,6 +272,7 @@ HMSE_API int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_
     unsigned long long* min_gid = (unsigned long long*)(table + cap);
     HMSE_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t) + m * sizeof(uint64_t), st));
     const unsigned grid = (unsigned)div_up64(m, 256);
+    HT_BEGIN(ctx, HT_DEDUP, st);
     KL(ctx);
     dedup_insert_kernel<<<grid, 256, 0, st>>>(d_records, 40, m, table, cap - 1);
     KL(ctx);
@@ -279,6 +280,7 @@ HMSE_API int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_
     KL(ctx);
     read_gid_kernel<<<grid, 256, 0, st>>>(d_records, m, table, cap - 1, min_gid, d_canon_gid);
     HMSE_LAUNCH_CHECK(ctx);
+    HT_END(ctx, HT_DEDUP, st);
     return HMSE_OK;
 }
 
