@@ -31,11 +31,15 @@ using namespace dfl;
 
 namespace {
 
-constexpr int OWN_CAP = 8;        // nearest own-chunk candidates examined per position
-constexpr int DICT_CAP = 8;       // nearest dictionary candidates examined per position (2 batches of 4)
+constexpr int OWN_CAP = 4;        // nearest own-chunk candidates examined per position
+constexpr int DICT_CAP = 4;       // nearest dictionary candidates examined per position (one prefetched batch)
+constexpr int DICT_HASH_BITS = 15; // the dictionary index lives in global memory: finer buckets, fewer false candidates
+constexpr uint32_t DICT_BUCKETS = 1u << DICT_HASH_BITS;
 constexpr uint32_t DICT_MAX = 32768;
 constexpr uint32_t NMAX_SMALL = 12288, NMAX_LARGE = 32768;
 constexpr int T_PARSE = 512;
+constexpr int TILE_SHIFT = 9;       // log2(T_PARSE): a scatter tile is T_PARSE consecutive positions
+static_assert((1 << TILE_SHIFT) == T_PARSE, "TILE_SHIFT");
 constexpr int T_ENCODE = 256;
 constexpr int HUFF_WARPS = 8;
 constexpr uint32_t BATCH_SMALL = 32768, BATCH_LARGE = 8192;  // chunks per batch (bounds the token scratch)
@@ -49,8 +53,8 @@ struct DictEnt {   // 16 bytes: a match of up to 8 bytes is decided without touc
     uint32_t pad;
 };
 struct DictDev {
-    uint8_t bytes[DICT_MAX + 16];
-    uint16_t boff[NBUCKET + 8];  // bucket h = ent[boff[h] .. boff[h+1]), nearest (largest pos) first
+    uint8_t bytes[DICT_MAX + 32];
+    uint16_t boff[DICT_BUCKETS + 8];  // bucket h = ent[boff[h] .. boff[h+1]), nearest (largest pos) first
     DictEnt ent[DICT_MAX];
 };
 
@@ -107,6 +111,9 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t adler_a, adler_b;
 };
 
+// Dictionary bucket of a 4-byte value; the own-chunk bucket hash4(v) is its top HASH_BITS bits.
+__host__ __device__ __forceinline__ uint32_t hash_dict(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - DICT_HASH_BITS); }
+
 __device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t off) {
     const uint32_t i = off >> 2;
     return __funnelshift_r(w[i], w[i + 1], (off & 3) * 8);
@@ -146,27 +153,45 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, u
     return r;
 }
 
-// Common-prefix length of chunk[p+l ..] and chunk[q+l ..] continuing from l (both in shared memory).
+// Common-prefix length of chunk[p+l ..] and chunk[q+l ..] continuing from l (both in shared memory),
+// 8 bytes per step (the four loads of a step are independent).
 __device__ __forceinline__ uint32_t extend_own(const uint32_t* d32, uint32_t p, uint32_t q, uint32_t l, uint32_t lim) {
     while (l < lim) {
-        const uint32_t x = ld32u(d32, p + l) ^ ld32u(d32, q + l);
-        if (x) {
-            l += (uint32_t)(__ffs((int)x) - 1) >> 3;
+        const uint32_t x0 = ld32u(d32, p + l) ^ ld32u(d32, q + l);
+        const uint32_t x1 = ld32u(d32, p + l + 4) ^ ld32u(d32, q + l + 4);
+        if (x0) {
+            l += (uint32_t)(__ffs((int)x0) - 1) >> 3;
             break;
         }
-        l += 4;
+        if (x1) {
+            l += 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+            break;
+        }
+        l += 8;
     }
     return l > lim ? lim : l;
 }
+// Same against the dictionary text in global memory, 16 bytes per step: one L2 round trip covers
+// the whole match for ordinary words.
 __device__ __forceinline__ uint32_t extend_dict(const uint32_t* d32, const uint8_t* dict, uint32_t p, uint32_t j,
                                                 uint32_t l, uint32_t lim) {
     while (l < lim) {
-        const uint32_t x = ld32u(d32, p + l) ^ ldg32u(dict, j + l);
-        if (x) {
-            l += (uint32_t)(__ffs((int)x) - 1) >> 3;
-            break;
+        uint32_t g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) g[u] = ldg32u(dict, j + l + 4 * u);
+        bool stop = false;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (stop) continue;
+            const uint32_t x = ld32u(d32, p + l) ^ g[u];
+            if (x) {
+                l += (uint32_t)(__ffs((int)x) - 1) >> 3;
+                stop = true;
+            } else {
+                l += 4;
+            }
         }
-        l += 4;
+        if (stop) break;
     }
     return l > lim ? lim : l;
 }
@@ -293,9 +318,11 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 __syncthreads();
             }
             PROF(3)
-            // Buckets are already ordered except for same-hash positions inside one scatter tile
-            // (common in text: a word repeated within 512 bytes).  Odd-even transposition passes over
-            // all adjacent same-bucket pairs put them in order; groups are tiny, so 2-4 passes do.
+            // Buckets are already ordered except for same-hash positions that were scattered in the same
+            // tile (common in text: a word repeated within 512 bytes).  Such a group is contiguous in the
+            // bucket; every element finds its rank inside its group (groups are tiny) and is rewritten
+            // in place through a temporary copy.
+            uint16_t* s_tmp16 = reinterpret_cast<uint16_t*>(mptr);   // match words are not written before P4
             for (uint32_t i = t; i < (nmax >> 5); i += T) s_flag[i] = 0;   // bit i: sorted index i starts a bucket
             __syncthreads();
             for (uint32_t i = 0; i < per; i++) {
@@ -304,23 +331,27 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 if (s_E[h + 1] > b0) atomicOr(&s_flag[b0 >> 5], 1u << (b0 & 31));
             }
             __syncthreads();
-            for (;;) {
-                int changed = 0;
-#pragma unroll
-                for (int parity = 0; parity < 2; parity++) {
-                    for (uint32_t i = 2 * t + parity; i + 1 < nh; i += 2 * T) {
-                        if ((s_flag[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u) continue;  // i+1 starts another bucket
-                        const uint16_t x = s_sorted[i], y = s_sorted[i + 1];
-                        if (x > y) {
-                            s_sorted[i] = y;
-                            s_sorted[i + 1] = x;
-                            changed = 1;
-                        }
-                    }
-                    __syncthreads();
+            for (uint32_t i = t; i < nh; i += T) {
+                const uint32_t p = s_sorted[i];
+                const uint32_t tile = p >> TILE_SHIFT;
+                uint32_t first = i, smaller = 0;
+                // left neighbours of the same bucket and tile
+                for (uint32_t j = i; j > 0 && !((s_flag[j >> 5] >> (j & 31)) & 1u);) {
+                    j--;
+                    const uint32_t q = s_sorted[j];
+                    if ((q >> TILE_SHIFT) != tile) break;
+                    first = j;
+                    smaller += q < p;
                 }
-                if (!__syncthreads_or(changed)) break;
+                for (uint32_t j = i + 1; j < nh && !((s_flag[j >> 5] >> (j & 31)) & 1u); j++) {
+                    const uint32_t q = s_sorted[j];
+                    if ((q >> TILE_SHIFT) != tile) break;
+                    smaller += q < p;
+                }
+                s_tmp16[first + smaller] = (uint16_t)p;
             }
+            __syncthreads();
+            for (uint32_t i = t; i < nh; i += T) s_sorted[i] = s_tmp16[i];
             __syncthreads();
             PROF(4)
             if (t < 3 && t < n) mptr[SK(n - 1 - t)] = 0;  // the last 3 positions cannot start a match
@@ -339,10 +370,11 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     if (i < nh) {
                         r.p = s_sorted[i];
                         r.v = ld32u(s_data32, r.p);
-                        r.h = hash4(r.v);
+                        const uint32_t hd = hash_dict(r.v);
+                        r.h = hd >> (DICT_HASH_BITS - HASH_BITS);
                         if (use_dict) {
-                            r.d0 = __ldg(&a.dict->boff[r.h]);
-                            r.d1 = __ldg(&a.dict->boff[r.h + 1]);
+                            r.d0 = __ldg(&a.dict->boff[hd]);
+                            r.d1 = __ldg(&a.dict->boff[hd + 1]);
                         }
                     }
                     return r;
@@ -351,7 +383,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 uint4 e1[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) e1[u] = s0.d0 + u < s0.d1 ? __ldg(ent + s0.d0 + u) : make_uint4(~s0.v, 0, 0, 0);
-                for (uint32_t i = t; i < nh; i += T) {
+                for (uint32_t ib = warp * 32; ib < nh; ib += T) {   // warp-uniform trip count
+                    const uint32_t i = ib + lane;
+                    const bool act = i < nh;
                     const StA cur = s0;
                     uint4 e[4];
 #pragma unroll
@@ -362,48 +396,54 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     for (int u = 0; u < 4; u++) e1[u] = s0.d0 + u < s0.d1 ? __ldg(ent + s0.d0 + u) : make_uint4(~s0.v, 0, 0, 0);
 
                     const uint32_t p = cur.p, v = cur.v, h = cur.h;
-                    const uint32_t maxl = n - p < (uint32_t)MAX_MATCH ? n - p : (uint32_t)MAX_MATCH;
-                    const uint32_t b0 = s_E[h];
+                    const uint32_t maxl = act ? (n - p < (uint32_t)MAX_MATCH ? n - p : (uint32_t)MAX_MATCH) : 0u;
+                    const uint32_t b0 = act ? (uint32_t)s_E[h] : 0xffffffffu;
                     uint32_t best = 3, bdist = 0;
-                    const uint32_t stop = i > b0 + OWN_CAP ? i - OWN_CAP : b0;
-                    for (uint32_t c = i; c-- > stop;) {
-                        const uint32_t q = s_sorted[c];
-                        if (ld32u(s_data32, q) != v) continue;
-                        const uint32_t l = extend_own(s_data32, p, q, 4, maxl);
-                        if (l > best) {
-                            best = l;
-                            bdist = p - q;
-                            if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
+                    bool fin = !act;
+                    // Own candidates are the preceding sorted indices, i.e. the preceding LANES: their
+                    // position and first four bytes come by shuffle; only candidates that belong to the
+                    // previous warp-iteration (lane < d) are read from shared memory.
+#pragma unroll
+                    for (int d = 1; d <= OWN_CAP; d++) {
+                        uint32_t q = __shfl_up_sync(0xffffffffu, p, d);
+                        uint32_t vq = __shfl_up_sync(0xffffffffu, v, d);
+                        const bool valid = !fin && i >= b0 + (uint32_t)d;
+                        if (valid && lane < (unsigned)d) {
+                            q = s_sorted[i - d];
+                            vq = ld32u(s_data32, q);
+                        }
+                        if (valid && vq == v && (best < 4 || s_data[q + best] == s_data[p + best])) {
+                            const uint32_t l = extend_own(s_data32, p, q, 4, maxl);
+                            if (l > best) {
+                                best = l;
+                                bdist = p - q;
+                                if (best >= (uint32_t)NICE_LENGTH || best == maxl) fin = true;
+                            }
                         }
                     }
+                    if (!act) continue;
                     if (use_dict && best < (uint32_t)NICE_LENGTH && best < maxl) {
                         const uint32_t nx = ld32u(s_data32, p + 4);
                         bool done = false;
-                        for (uint32_t bi = cur.d0; bi < cur.d1 && bi < cur.d0 + DICT_CAP && !done; bi += 4) {
-                            if (bi != cur.d0) {
 #pragma unroll
-                                for (int u = 0; u < 4; u++) e[u] = bi + u < cur.d1 ? __ldg(ent + bi + u) : make_uint4(~v, 0, 0, 0);
+                        for (int u = 0; u < DICT_CAP; u++) {
+                            if (done || e[u].x != v) continue;
+                            const uint32_t jpos = e[u].z;
+                            const uint32_t dist = p + a.dict_len - jpos;
+                            if (dist > (uint32_t)WSIZE) {  // farther entries are only farther
+                                done = true;
+                                continue;
                             }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                if (done || e[u].x != v) continue;
-                                const uint32_t jpos = e[u].z;
-                                const uint32_t dist = p + a.dict_len - jpos;
-                                if (dist > (uint32_t)WSIZE) {  // farther entries are only farther
-                                    done = true;
-                                    continue;
-                                }
-                                uint32_t lim = a.dict_len - jpos;  // matches do not run from the dictionary into the chunk
-                                if (lim > maxl) lim = maxl;
-                                const uint32_t x = e[u].y ^ nx;
-                                uint32_t l = x ? 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3) : 8;
-                                if (l > lim) l = lim;
-                                if (l == 8 && lim > 8) l = extend_dict(s_data32, a.dict->bytes, p, jpos, 8, lim);
-                                if (l > best) {
-                                    best = l;
-                                    bdist = dist;
-                                    if (best >= (uint32_t)NICE_LENGTH || best == maxl) done = true;
-                                }
+                            uint32_t lim = a.dict_len - jpos;  // matches do not run from the dictionary into the chunk
+                            if (lim > maxl) lim = maxl;
+                            const uint32_t x = e[u].y ^ nx;
+                            uint32_t l = x ? 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3) : 8;
+                            if (l > lim) l = lim;
+                            if (l == 8 && lim > 8) l = extend_dict(s_data32, a.dict->bytes, p, jpos, 8, lim);
+                            if (l > best) {
+                                best = l;
+                                bdist = dist;
+                                if (best >= (uint32_t)NICE_LENGTH || best == maxl) done = true;
                             }
                         }
                     }
@@ -443,23 +483,30 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 uint16_t* s_bexit = s_E;          // [block][258]: exit of a chain entering the block at offset o (E is dead)
                 uint16_t* s_bentry = sm->bentry;  // [block]: true entry position (0xFFFF = not visited)
                 const uint32_t NB = (n + 1023) >> 10;
-                // (a) entries into a block lie in its first 258 positions (a match is <= 258 long)
-                for (uint32_t blk = warp; blk < NB; blk += nwarps) {
+                // (a) a chain almost always enters a block within its first 64 positions (only a match
+                //     longer than that jumps further); those 64 entry points are tabulated in parallel
+                for (uint32_t item = warp; item < 2 * NB; item += nwarps) {
+                    const uint32_t blk = item >> 1, o = ((item & 1) << 5) + lane;
                     const uint32_t bs = blk << 10, be = (bs + 1024 < n) ? bs + 1024 : n;
-                    for (uint32_t o = lane; o < 258 && bs + o < be; o += 32) {
+                    if (bs + o < be) {
                         uint32_t p = bs + o;
                         while (p < be) p = s_exit[SK(p)];
-                        s_bexit[blk * 258 + o] = (uint16_t)p;
+                        s_bexit[blk * 64 + o] = (uint16_t)p;
                     }
-                    if (lane == 0) s_bentry[blk] = 0xFFFF;
+                    if ((item & 1) == 0 && lane == 0) s_bentry[blk] = 0xFFFF;
                 }
                 __syncthreads();
                 if (t == 0) {  // (b)
                     uint32_t p = 0;
                     while (p < n) {
-                        const uint32_t blk = p >> 10;
+                        const uint32_t blk = p >> 10, o = p & 1023;
                         s_bentry[blk] = (uint16_t)p;
-                        p = s_bexit[blk * 258 + (p & 1023)];
+                        if (o < 64) {
+                            p = s_bexit[blk * 64 + o];
+                        } else {  // rare: walk this block directly
+                            const uint32_t be = ((blk << 10) + 1024 < n) ? (blk << 10) + 1024 : n;
+                            while (p < be) p = s_exit[SK(p)];
+                        }
                     }
                 }
                 __syncthreads();
@@ -1024,16 +1071,16 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
     if (!img) HMSE_FAIL(ctx, HMSE_E_NOMEM, "dictionary index");
     memcpy(img->bytes, tmp, dict_len);
     const uint32_t nh = dict_len >= 4 ? dict_len - 3 : 0;
-    uint32_t* cnt = (uint32_t*)calloc(NBUCKET + 1, sizeof(uint32_t));
+    uint32_t* cnt = (uint32_t*)calloc(DICT_BUCKETS + 1, sizeof(uint32_t));
     auto le32 = [&](uint32_t j) {
         return (uint32_t)tmp[j] | ((uint32_t)tmp[j + 1] << 8) | ((uint32_t)tmp[j + 2] << 16) | ((uint32_t)tmp[j + 3] << 24);
     };
-    for (uint32_t j = 0; j < nh; j++) cnt[hash4(le32(j)) + 1]++;
-    for (uint32_t h = 0; h < NBUCKET; h++) cnt[h + 1] += cnt[h];
-    for (uint32_t h = 0; h <= NBUCKET; h++) img->boff[h] = (uint16_t)cnt[h];
+    for (uint32_t j = 0; j < nh; j++) cnt[hash_dict(le32(j)) + 1]++;
+    for (uint32_t h = 0; h < DICT_BUCKETS; h++) cnt[h + 1] += cnt[h];
+    for (uint32_t h = 0; h <= DICT_BUCKETS; h++) img->boff[h] = (uint16_t)cnt[h];
     // descending position inside a bucket: walk positions from the end
     for (uint32_t j = nh; j-- > 0;) {
-        const uint32_t v = le32(j), h = hash4(v);
+        const uint32_t v = le32(j), h = hash_dict(v);
         const uint32_t i = cnt[h]++;
         img->ent[i].first4 = v;
         uint32_t nx = 0;

@@ -17,6 +17,7 @@ struct Params {
     int chain_dict;   // max dictionary candidates examined
     int lazy;         // 0 greedy, 1 zlib-style lazy
     int too_far;      // drop length-3 matches farther than this (0 = keep)
+    int dict_hash_bits;  // buckets of the dictionary index (the own-chunk index uses HASH_BITS)
 };
 
 static inline uint32_t rd(const uint8_t* p, int nb) {
@@ -37,8 +38,10 @@ static uint32_t adler32(const uint8_t* d, uint64_t n) {
 extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t* dict, uint32_t dict_len,
                                   const Params* pr, uint8_t* out, uint64_t cap, uint32_t* stats) {
     const int HB = pr->hash_bytes;
-    std::vector<std::vector<uint32_t>> own(NBUCKET), dic(NBUCKET);
-    for (uint32_t j = 0; j + HB <= dict_len; j++) dic[hash4(rd(dict + j, HB))].push_back(j);
+    const int DB = pr->dict_hash_bits ? pr->dict_hash_bits : HASH_BITS;
+    auto dhash = [&](uint32_t v) { return (v * 0x9E3779B1u) >> (32 - DB); };
+    std::vector<std::vector<uint32_t>> own(NBUCKET), dic((size_t)1 << DB);
+    for (uint32_t j = 0; j + HB <= dict_len; j++) dic[dhash(rd(dict + j, HB))].push_back(j);
     std::vector<uint16_t> mlen(n + 1, 0), mdist(n + 1, 0);
     for (uint32_t p = 0; p < n; p++) {
         uint32_t best = 0, bdist = 0;
@@ -54,7 +57,7 @@ extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t
                 if (l > best) { best = l; bdist = p - q; }
                 if (best >= (uint32_t)NICE_LENGTH || best == maxl) break;
             }
-            auto& db = dic[h];
+            auto& db = dic[dhash(rd(data + p, HB))];
             ex = 0;
             if (best < (uint32_t)NICE_LENGTH && best < maxl)
                 for (int i = (int)db.size() - 1; i >= 0 && ex < pr->chain_dict; i--, ex++) {
