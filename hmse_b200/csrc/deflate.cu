@@ -32,7 +32,7 @@ using namespace dfl;
 namespace {
 
 constexpr int OWN_CAP = 4;        // nearest own-chunk candidates examined per position
-constexpr int DICT_CAP = 4;       // nearest dictionary candidates examined per position (one prefetched batch)
+constexpr int DICT_CAP = 4;       // nearest dictionary candidates examined per position (one 16-byte bucket record)
 constexpr int DICT_HASH_BITS = 15; // the dictionary index lives in global memory: finer buckets, fewer false candidates
 constexpr uint32_t DICT_BUCKETS = 1u << DICT_HASH_BITS;
 constexpr uint32_t DICT_MAX = 32768;
@@ -46,16 +46,14 @@ constexpr uint32_t BATCH_SMALL = 32768, BATCH_LARGE = 8192;  // chunks per batch
 constexpr uint32_t REC_WORDS = 320;                          // 288 lit/len + 32 dist counters / codes
 
 // Device image of the dictionary index (SLOT_DEFLATE_DICT), built on the host once per dictionary.
-struct DictEnt {   // 16 bytes: a match of up to 8 bytes is decided without touching the dictionary text
-    uint32_t first4;  // le32 at pos
-    uint32_t next4;   // le32 at pos + 4 (zero padded past the end)
-    uint32_t pos;
-    uint32_t pad;
-};
+// One 16-byte record per bucket of 4-byte hashes: the four nearest (largest position first) dictionary
+// positions of that bucket, each as  valid << 31 | tag << 23 | prev << 15 | pos  where tag = eight more
+// bits of the hash (a filter: phase B compares the real bytes) and prev = the byte before pos
+// (DICT_PREV0 before position 0).  One LDG.128 per chunk position screens all four candidates.
+constexpr uint32_t DICT_PREV0 = 0xFFu, CHUNK_PREV0 = 0xFEu;   // never equal: (0, 0) is always a run head
 struct DictDev {
     uint8_t bytes[DICT_MAX + 32];
-    uint16_t boff[DICT_BUCKETS + 8];  // bucket h = ent[boff[h] .. boff[h+1]), nearest (largest pos) first
-    DictEnt ent[DICT_MAX];
+    uint4 bk4[DICT_BUCKETS];
 };
 
 // Per-chunk record handed from kernel to kernel (indexed by job within the batch).
@@ -101,7 +99,9 @@ __device__ unsigned long long g_prof[16];
         tprev = now__;                                              \
     }
 
-constexpr uint32_t CNT_WORDS = NBUCKET / 2 + 36;  // bucket table; later the 32 x 258 block-exit table
+constexpr uint32_t CNT_WORDS = NBUCKET / 2 + 36;  // bucket table; later the pair lists, then the 32 x 64 block-exit table
+constexpr uint32_t PAIR_CAP = 256;                // per-warp list of pairs awaiting extension: < 32 left over + 8 x 28 new
+static_assert(PAIR_CAP * (T_PARSE / 32) <= CNT_WORDS, "pair lists must fit in the bucket table");
 
 struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t hist[REC_WORDS];
@@ -113,6 +113,10 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
 
 // Dictionary bucket of a 4-byte value; the own-chunk bucket hash4(v) is its top HASH_BITS bits.
 __host__ __device__ __forceinline__ uint32_t hash_dict(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - DICT_HASH_BITS); }
+// the next eight bits of the same product, placed where the bucket records keep their tag (bits 23..30)
+__host__ __device__ __forceinline__ uint32_t dict_tag23(uint32_t v) {
+    return ((v * 0x9E3779B1u) << (DICT_HASH_BITS - 1)) & 0x7f800000u;
+}
 
 __device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t off) {
     const uint32_t i = off >> 2;
@@ -153,12 +157,45 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, u
     return r;
 }
 
-// Common-prefix length of chunk[p+l ..] and chunk[q+l ..] continuing from l (both in shared memory),
-// 8 bytes per step (the four loads of a step are independent).
-__device__ __forceinline__ uint32_t extend_own(const uint32_t* d32, uint32_t p, uint32_t q, uint32_t l, uint32_t lim) {
+// Exclusive prefix MAX of one u32 per thread (identity 0).  tmp = 33 words of shared memory.
+__device__ __forceinline__ uint32_t block_excl_scan_max(uint32_t v, uint32_t* tmp) {
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc = max(inc, t);
+    }
+    uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 0;
+    __syncthreads();
+    if (lane == 31) tmp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t s = lane < nw ? tmp[lane] : 0;
+        uint32_t si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= (unsigned)o) si = max(si, t);
+        }
+        uint32_t se = __shfl_up_sync(0xffffffffu, si, 1);
+        if (lane == 0) se = 0;
+        tmp[lane] = se;
+    }
+    __syncthreads();
+    const uint32_t r = max(exc, tmp[w]);
+    __syncthreads();
+    return r;
+}
+
+// Length of the common prefix of chunk[p ..] (shared memory words d32) and src[q ..] (generic pointer: the
+// chunk itself or the dictionary text), continuing from l, at most lim; 8 bytes per step.
+__device__ __forceinline__ uint32_t extend_run(const uint32_t* d32, const uint32_t* src, uint32_t p, uint32_t q,
+                                               uint32_t l, uint32_t lim) {
     while (l < lim) {
-        const uint32_t x0 = ld32u(d32, p + l) ^ ld32u(d32, q + l);
-        const uint32_t x1 = ld32u(d32, p + l + 4) ^ ld32u(d32, q + l + 4);
+        const uint32_t x0 = ld32u(d32, p + l) ^ ld32u(src, q + l);
+        const uint32_t x1 = ld32u(d32, p + l + 4) ^ ld32u(src, q + l + 4);
         if (x0) {
             l += (uint32_t)(__ffs((int)x0) - 1) >> 3;
             break;
@@ -168,30 +205,6 @@ __device__ __forceinline__ uint32_t extend_own(const uint32_t* d32, uint32_t p, 
             break;
         }
         l += 8;
-    }
-    return l > lim ? lim : l;
-}
-// Same against the dictionary text in global memory, 16 bytes per step: one L2 round trip covers
-// the whole match for ordinary words.
-__device__ __forceinline__ uint32_t extend_dict(const uint32_t* d32, const uint8_t* dict, uint32_t p, uint32_t j,
-                                                uint32_t l, uint32_t lim) {
-    while (l < lim) {
-        uint32_t g[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) g[u] = ldg32u(dict, j + l + 4 * u);
-        bool stop = false;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (stop) continue;
-            const uint32_t x = ld32u(d32, p + l) ^ g[u];
-            if (x) {
-                l += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                stop = true;
-            } else {
-                l += 4;
-            }
-        }
-        if (stop) break;
     }
     return l > lim ? lim : l;
 }
@@ -354,101 +367,109 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             for (uint32_t i = t; i < nh; i += T) s_sorted[i] = s_tmp16[i];
             __syncthreads();
             PROF(4)
-            if (t < 3 && t < n) mptr[SK(n - 1 - t)] = 0;  // the last 3 positions cannot start a match
-            // ---- P4: best match of every position.  One thread per SORTED index: the lanes of a
-            //      warp work on the same or neighbouring buckets (similar chain lengths, broadcast
-            //      loads).  Nearest candidate first, strictly longer wins (zlib's rule).  Dictionary
-            //      loads run two positions ahead (bucket bounds) and one ahead (first 4 entries), so
-            //      their L2 latency overlaps the shared-memory search of the current position. -------
+            // ---- P4: matches as RUNS.  A pair (position p, source q) whose four bytes agree and whose
+            //      preceding bytes differ starts a run: every position p+k inside it has a match of
+            //      length end-(p+k) at the same distance, so only run heads are extended and
+            //      best[p] = (prefix max over start positions of the run ends) - p  (P4c below).
+            //      Phase A, one lane per SORTED index (windows of 28 + 4 lanes of context), is a pure
+            //      screen: the four nearest own candidates are the four preceding lanes (their bytes
+            //      come by shuffle), the four nearest dictionary candidates come in one 16-byte bucket
+            //      record.  The surviving (position, source) pairs are compacted into a per-warp list and
+            //      extended 32 at a time (phase B), so the byte comparison runs with full warps instead
+            //      of the few lanes that happen to hold a candidate.
+            for (uint32_t i = t; i < n + (n >> 5); i += T) mptr[i] = 0;   // run keys: end << 15 | (32768 - dist)
+            __syncthreads();
             {
-                const uint4* ent = reinterpret_cast<const uint4*>(a.dict->ent);
+                const uint32_t* dictw = reinterpret_cast<const uint32_t*>(a.dict->bytes);
                 const bool use_dict = a.dict_len != 0;
-                struct StA { uint32_t p, v, h, d0, d1; };
-                auto stageA = [&](uint32_t i) {
+                uint32_t* plist = s_cnt32 + warp * PAIR_CAP;   // the bucket table is dead: E is not needed to walk s_sorted
+                uint32_t pcnt = 0;                             // warp-uniform
+                const uint32_t nwin = (nh + 27) / 28;
+                struct StA { uint32_t pp, v; uint4 bk; };
+                // pp = position | previous byte << 16; lanes outside the index range carry pp = ~0
+                auto stageA = [&](uint32_t w) {
                     StA r;
-                    r.p = 0xffffffffu; r.v = 0; r.h = 0; r.d0 = 0; r.d1 = 0;
-                    if (i < nh) {
-                        r.p = s_sorted[i];
-                        r.v = ld32u(s_data32, r.p);
-                        const uint32_t hd = hash_dict(r.v);
-                        r.h = hd >> (DICT_HASH_BITS - HASH_BITS);
-                        if (use_dict) {
-                            r.d0 = __ldg(&a.dict->boff[hd]);
-                            r.d1 = __ldg(&a.dict->boff[hd + 1]);
-                        }
+                    r.pp = 0xffffffffu; r.v = 0; r.bk = make_uint4(0, 0, 0, 0);
+                    const int i = (int)(28 * w) - 4 + (int)lane;
+                    if (w < nwin && i >= 0 && i < (int)nh) {
+                        const uint32_t p = s_sorted[i];
+                        r.v = ld32u(s_data32, p);
+                        r.pp = p | ((p ? (uint32_t)s_data[p - 1] : CHUNK_PREV0) << 16);
+                        if (use_dict && lane >= 4) r.bk = __ldg(&a.dict->bk4[hash_dict(r.v)]);
                     }
                     return r;
                 };
-                StA s0 = stageA(t), s1 = stageA(t + T);
-                uint4 e1[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) e1[u] = s0.d0 + u < s0.d1 ? __ldg(ent + s0.d0 + u) : make_uint4(~s0.v, 0, 0, 0);
-                for (uint32_t ib = warp * 32; ib < nh; ib += T) {   // warp-uniform trip count
-                    const uint32_t i = ib + lane;
-                    const bool act = i < nh;
+                auto extend_pairs = [&](uint32_t first, uint32_t count) {   // phase B on plist[first .. first+count)
+                    if (lane < count) {
+                        const uint32_t rec = plist[first + lane];
+                        const uint32_t p = rec & 0x7fffu, src = rec >> 16;
+                        const bool isd = (rec & 0x8000u) != 0;
+                        uint32_t lim = n - p, dist = p - src;
+                        const uint32_t* sw = s_data32;
+                        if (isd) {
+                            lim = min(lim, a.dict_len - src);   // matches do not run from the dictionary into the chunk
+                            dist = p + a.dict_len - src;
+                            sw = dictw;
+                        }
+                        const uint32_t l = extend_run(s_data32, sw, p, src, 0, lim);   // from 0: dictionary tags are only a filter
+                        if (l >= 4) atomicMax(&mptr[SK(p)], ((p + l) << 15) | (32768u - dist));
+                    }
+                };
+                StA s0 = stageA(warp), s1 = stageA(warp + nwarps);
+                for (uint32_t w = warp; w < nwin; w += nwarps) {   // warp-uniform trip count
                     const StA cur = s0;
-                    uint4 e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) e[u] = e1[u];
                     s0 = s1;
-                    s1 = stageA(i + 2 * T);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) e1[u] = s0.d0 + u < s0.d1 ? __ldg(ent + s0.d0 + u) : make_uint4(~s0.v, 0, 0, 0);
+                    s1 = stageA(w + 2 * nwarps);
 
-                    const uint32_t p = cur.p, v = cur.v, h = cur.h;
-                    const uint32_t maxl = act ? (n - p < (uint32_t)MAX_MATCH ? n - p : (uint32_t)MAX_MATCH) : 0u;
-                    const uint32_t b0 = act ? (uint32_t)s_E[h] : 0xffffffffu;
-                    uint32_t best = 3, bdist = 0;
-                    bool fin = !act;
-                    // Own candidates are the preceding sorted indices, i.e. the preceding LANES: their
-                    // position and first four bytes come by shuffle; only candidates that belong to the
-                    // previous warp-iteration (lane < d) are read from shared memory.
+                    const int i = (int)(28 * w) - 4 + (int)lane;
+                    const bool act = lane >= 4 && i < (int)nh;
+                    const uint32_t p = cur.pp & 0x7fffu;
+                    uint32_t rec[OWN_CAP + DICT_CAP];
+                    uint32_t mask = 0;
 #pragma unroll
                     for (int d = 1; d <= OWN_CAP; d++) {
-                        uint32_t q = __shfl_up_sync(0xffffffffu, p, d);
-                        uint32_t vq = __shfl_up_sync(0xffffffffu, v, d);
-                        const bool valid = !fin && i >= b0 + (uint32_t)d;
-                        if (valid && lane < (unsigned)d) {
-                            q = s_sorted[i - d];
-                            vq = ld32u(s_data32, q);
-                        }
-                        if (valid && vq == v && (best < 4 || s_data[q + best] == s_data[p + best])) {
-                            const uint32_t l = extend_own(s_data32, p, q, 4, maxl);
-                            if (l > best) {
-                                best = l;
-                                bdist = p - q;
-                                if (best >= (uint32_t)NICE_LENGTH || best == maxl) fin = true;
-                            }
-                        }
+                        const uint32_t ppq = __shfl_up_sync(0xffffffffu, cur.pp, d);
+                        const uint32_t vq = __shfl_up_sync(0xffffffffu, cur.v, d);
+                        // same four bytes (hence same bucket, earlier position), different byte before: a run starts here
+                        if (act && vq == cur.v && ((ppq ^ cur.pp) >> 16) != 0 && ppq != 0xffffffffu) mask |= 1u << (d - 1);
+                        rec[d - 1] = p | (ppq << 16);
                     }
-                    if (!act) continue;
-                    if (use_dict && best < (uint32_t)NICE_LENGTH && best < maxl) {
-                        const uint32_t nx = ld32u(s_data32, p + 4);
-                        bool done = false;
+                    if (use_dict) {
+                        const uint32_t my = dict_tag23(cur.v) | ((cur.pp >> 16) << 15);
+                        const uint32_t c[4] = {cur.bk.x, cur.bk.y, cur.bk.z, cur.bk.w};
 #pragma unroll
                         for (int u = 0; u < DICT_CAP; u++) {
-                            if (done || e[u].x != v) continue;
-                            const uint32_t jpos = e[u].z;
-                            const uint32_t dist = p + a.dict_len - jpos;
-                            if (dist > (uint32_t)WSIZE) {  // farther entries are only farther
-                                done = true;
-                                continue;
-                            }
-                            uint32_t lim = a.dict_len - jpos;  // matches do not run from the dictionary into the chunk
-                            if (lim > maxl) lim = maxl;
-                            const uint32_t x = e[u].y ^ nx;
-                            uint32_t l = x ? 4 + ((uint32_t)(__ffs((int)x) - 1) >> 3) : 8;
-                            if (l > lim) l = lim;
-                            if (l == 8 && lim > 8) l = extend_dict(s_data32, a.dict->bytes, p, jpos, 8, lim);
-                            if (l > best) {
-                                best = l;
-                                bdist = dist;
-                                if (best >= (uint32_t)NICE_LENGTH || best == maxl) done = true;
-                            }
+                            const uint32_t x = c[u] ^ my;   // valid, same tag, different previous byte, inside the window
+                            const uint32_t j = c[u] & 0x7fffu;
+                            if (act && (int32_t)c[u] < 0 && (x & 0x7f800000u) == 0 && (x & 0x007f8000u) != 0 &&
+                                p + a.dict_len - j <= (uint32_t)WSIZE)
+                                mask |= 16u << u;
+                            rec[OWN_CAP + u] = p | 0x8000u | (j << 16);
                         }
                     }
-                    mptr[SK(p)] = best >= 4 ? (best << 16) | (bdist - 1) : 0u;
+                    if (__any_sync(0xffffffffu, mask != 0)) {
+                        // compaction: exclusive scan of the per-lane pair counts
+                        const uint32_t c = __popc(mask);
+                        uint32_t inc = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= (unsigned)o) inc += tt;
+                        }
+                        uint32_t o = pcnt + inc - c;
+#pragma unroll
+                        for (int sl = 0; sl < OWN_CAP + DICT_CAP; sl++)
+                            if ((mask >> sl) & 1u) plist[o++] = rec[sl];
+                        pcnt += __shfl_sync(0xffffffffu, inc, 31);
+                        __syncwarp();
+                        while (pcnt >= 32) {
+                            pcnt -= 32;
+                            extend_pairs(pcnt, 32);
+                        }
+                        __syncwarp();
+                    }
                 }
+                if (pcnt) extend_pairs(0, pcnt);
             }
             __syncthreads();
             PROF(5)
@@ -457,6 +478,31 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             const uint32_t R = (n + 31) >> 5;
             const uint32_t rpt = (R + T - 1) / T;
             const uint32_t r0 = t * rpt, r1 = (r0 + rpt < R) ? r0 + rpt : R;
+            // ---- P4c: run keys -> match words: a forward prefix max over positions (thread-local over its
+            //      own ranges, one block scan of the per-thread maxima in between) ---------------------------
+            {
+                uint32_t loc = 0;
+                for (uint32_t r = r0; r < r1; r++) {
+                    const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
+                    for (uint32_t p = ps; p < pe; p++) loc = max(loc, mptr[SK(p)]);
+                }
+                uint32_t run = block_excl_scan_max(loc, sm->warp_tmp);
+                for (uint32_t r = r0; r < r1; r++) {
+                    const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
+                    for (uint32_t p = ps; p < pe; p++) {
+                        run = max(run, mptr[SK(p)]);
+                        const uint32_t end = run >> 15;
+                        uint32_t mw = 0;
+                        if (end >= p + 4) {
+                            const uint32_t L = min(end - p, (uint32_t)MAX_MATCH);
+                            mw = (L << 16) | (32767u - (run & 0x7fffu));
+                        }
+                        mptr[SK(p)] = mw;
+                    }
+                }
+            }
+            __syncthreads();
+            PROF(9)
             // ---- P5: backward DP: exit[p] = first chain position past p's range -------------
             for (uint32_t r = r0; r < r1; r++) {
                 const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
@@ -1071,26 +1117,18 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
     if (!img) HMSE_FAIL(ctx, HMSE_E_NOMEM, "dictionary index");
     memcpy(img->bytes, tmp, dict_len);
     const uint32_t nh = dict_len >= 4 ? dict_len - 3 : 0;
-    uint32_t* cnt = (uint32_t*)calloc(DICT_BUCKETS + 1, sizeof(uint32_t));
     auto le32 = [&](uint32_t j) {
         return (uint32_t)tmp[j] | ((uint32_t)tmp[j + 1] << 8) | ((uint32_t)tmp[j + 2] << 16) | ((uint32_t)tmp[j + 3] << 24);
     };
-    for (uint32_t j = 0; j < nh; j++) cnt[hash_dict(le32(j)) + 1]++;
-    for (uint32_t h = 0; h < DICT_BUCKETS; h++) cnt[h + 1] += cnt[h];
-    for (uint32_t h = 0; h <= DICT_BUCKETS; h++) img->boff[h] = (uint16_t)cnt[h];
-    // descending position inside a bucket: walk positions from the end
-    for (uint32_t j = nh; j-- > 0;) {
-        const uint32_t v = le32(j), h = hash_dict(v);
-        const uint32_t i = cnt[h]++;
-        img->ent[i].first4 = v;
-        uint32_t nx = 0;
-        for (uint32_t b = 0; b < 4; b++)
-            if (j + 4 + b < dict_len) nx |= (uint32_t)tmp[j + 4 + b] << (8 * b);
-        img->ent[i].next4 = nx;
-        img->ent[i].pos = j;
-        img->ent[i].pad = 0;
+    // ascending positions shift each bucket record by one slot: the largest DICT_CAP positions stay, nearest first
+    for (uint32_t j = 0; j < nh; j++) {
+        const uint32_t v = le32(j);
+        uint4& b = img->bk4[hash_dict(v)];
+        b.w = b.z;
+        b.z = b.y;
+        b.y = b.x;
+        b.x = 0x80000000u | dict_tag23(v) | ((j ? (uint32_t)tmp[j - 1] : DICT_PREV0) << 15) | j;
     }
-    free(cnt);
     cudaError_t e = cudaMemcpyAsync(dev, img, sizeof(DictDev), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     free(img);

@@ -18,6 +18,9 @@ struct Params {
     int lazy;         // 0 greedy, 1 zlib-style lazy
     int too_far;      // drop length-3 matches farther than this (0 = keep)
     int dict_hash_bits;  // buckets of the dictionary index (the own-chunk index uses HASH_BITS)
+    int mode;         // 0: every position extends its candidates; 1: run heads only + prefix max (skip a pair
+                      // only when the previous position examined its predecessor); 2: same, unconditional skip
+    int min_len;      // shortest match emitted (0 -> hash_bytes)
 };
 
 static inline uint32_t rd(const uint8_t* p, int nb) {
@@ -75,6 +78,89 @@ extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t
         if (best == 3 && pr->too_far && bdist > (uint32_t)pr->too_far) best = 0;
         mlen[p] = (uint16_t)best;
         mdist[p] = (uint16_t)(bdist - (best ? 1 : 0));  // stored as dist-1 so 32768 fits
+    }
+    if (pr->mode) {
+        // Run formulation: a verified pair (p, source s) whose preceding bytes differ starts a run that ends at
+        // `end`; every position inside it has a match of length end - p at the same distance, so
+        // best[p] = (prefix max of run ends over start positions) - p.
+        std::fill(mlen.begin(), mlen.end(), 0);
+        std::vector<uint32_t> prev_own, prev_dic, cur_own, cur_dic;
+        bool prev_sat = false, cur_sat = false;  // mode 3: a candidate list was cut short by its cap
+        uint64_t key_run = 0;  // end << 16 | (65535 - (dist-1))
+        uint64_t n_pairs = 0, n_heads = 0, steps_all = 0, steps_head = 0;
+        own.assign(NBUCKET, {});
+        const uint32_t minl = pr->min_len ? pr->min_len : HB;
+        for (uint32_t p = 0; p < n; p++) {
+            cur_own.clear();
+            cur_dic.clear();
+            cur_sat = false;
+            if (p + HB <= n) {
+                const uint32_t v = rd(data + p, HB);
+                auto& ob = own[hash4(v)];
+                if ((int)ob.size() > pr->chain_own || (int)dic[dhash(v)].size() > pr->chain_dict) cur_sat = true;
+                int ex = 0;
+                for (int i = (int)ob.size() - 1; i >= 0 && ex < pr->chain_own; i--, ex++) {
+                    const uint32_t q = ob[i];
+                    cur_own.push_back(q);
+                    if (rd(data + q, HB) != v) continue;
+                    n_pairs++;
+                    uint32_t l = 0;
+                    while (p + l < n && data[q + l] == data[p + l]) l++;
+                    steps_all += ((l < 258 ? l : 258) + 7) / 8;
+                    bool inh = p >= 1 && q >= 1 && data[p - 1] == data[q - 1];
+                    if (inh && pr->mode == 1) {
+                        bool found = false;
+                        for (uint32_t x : prev_own) found |= x == q - 1;
+                        inh = found;
+                    }
+                    if (inh && pr->mode == 3) inh = !prev_sat;
+                    if (inh) continue;
+                    n_heads++;
+                    steps_head += (l + 7) / 8;
+                    const uint64_t key = ((uint64_t)(p + l) << 16) | (65535 - (p - q - 1));
+                    if (key > key_run) key_run = key;
+                }
+                auto& db = dic[dhash(v)];
+                ex = 0;
+                for (int i = (int)db.size() - 1; i >= 0 && ex < pr->chain_dict; i--, ex++) {
+                    const uint32_t j = db[i];
+                    const uint32_t dist = p + dict_len - j;
+                    if (dist > WSIZE) break;
+                    cur_dic.push_back(j);
+                    if (rd(dict + j, HB) != v) continue;
+                    n_pairs++;
+                    uint32_t l = 0;
+                    while (p + l < n && j + l < dict_len && dict[j + l] == data[p + l]) l++;
+                    steps_all += ((l < 258 ? l : 258) + 7) / 8;
+                    bool inh = p >= 1 && j >= 1 && data[p - 1] == dict[j - 1];
+                    if (inh && pr->mode == 1) {
+                        bool found = false;
+                        for (uint32_t x : prev_dic) found |= x == j - 1;
+                        inh = found;
+                    }
+                    if (inh && pr->mode == 3) inh = !prev_sat;
+                    if (inh) continue;
+                    n_heads++;
+                    steps_head += (l + 7) / 8;
+                    const uint64_t key = ((uint64_t)(p + l) << 16) | (65535 - (dist - 1));
+                    if (key > key_run) key_run = key;
+                }
+                ob.push_back(p);
+            }
+            prev_own.swap(cur_own);
+            prev_dic.swap(cur_dic);
+            prev_sat = cur_sat;
+            const uint32_t end = (uint32_t)(key_run >> 16);
+            if (end >= p + minl) {
+                const uint32_t L = end - p < (uint32_t)MAX_MATCH ? end - p : (uint32_t)MAX_MATCH;
+                const uint32_t d1 = 65535 - (uint32_t)(key_run & 0xffff);
+                if (!(L == 3 && pr->too_far && d1 + 1 > (uint32_t)pr->too_far)) {
+                    mlen[p] = (uint16_t)L;
+                    mdist[p] = (uint16_t)d1;
+                }
+            }
+        }
+        if (stats) { stats[4] = (uint32_t)n_pairs; stats[5] = (uint32_t)n_heads; stats[6] = (uint32_t)steps_all; stats[7] = (uint32_t)steps_head; }
     }
     // parse
     std::vector<uint32_t> tok;  // literal: byte ; match: 1<<31 | len<<16 | (dist-1)
