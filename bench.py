@@ -34,6 +34,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gb", type=float, default=10.0, help="bytes per GPU per step, in GB (1e9)")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
+    ap.add_argument("--piece-mib", type=int, default=256, help="piece size of the streaming end-to-end path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -311,34 +312,56 @@ def run_ours(args):
                 "pipeline_frac": ((total + sum_over_ranks(out_bytes) + 40 * sum_over_ranks(n_chunks)) / (ms * 1e-3) / 1e9)
                 / (peak * world)}
 
+    uniq_chunks = sum_over_ranks(int(res.select.numel()))
+    tot_chunks = sum_over_ranks(n_chunks)
+    sel_b = sum_over_ranks(sel_bytes)
+    out_b = sum_over_ranks(out_bytes)
+
     # ---- end to end: pinned host input -> device -> results back on the host, every step ----------
     e2e = None
     if not args.no_e2e:
         host_in = torch.empty(n_avail, dtype=torch.uint8, pin_memory=True)
         host_in.copy_(d)
-        dbuf = ctx.empty(n_avail + 64, torch.uint8)[:n_avail]
-        cap_chunks = n_avail // cfg.min_size + 2
-        host_out = {"cuts": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
-                    "digests": torch.empty(cap_chunks * 32, dtype=torch.uint8, pin_memory=True),
-                    "canon": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
-                    "offsets": torch.empty(cap_chunks + 1, dtype=torch.int64, pin_memory=True),
-                    "blob": torch.empty(n_avail // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)}
         d2h = 0
+        if world == 1:
+            # one GPU: the streaming front end - pieces copied in while the previous piece is processed and
+            # the one before travels back (hmse_b200.IngestStream); results equal Ingest.run (tests/test_gpu_stream.py)
+            del d, res, cuts, starts, lens
+            torch.cuda.empty_cache()
+            stream_pipe = hmse_b200.IngestStream(ctx, cfg, zd, piece_bytes=args.piece_mib << 20)
+            api = ("hmse_b200.IngestStream.run(pinned host buffer): %d MiB pieces, host->device copy of piece k+1, pipeline "
+                   "on piece k and device->host copy of the results of piece k-1 (cuts, digests, canon, offsets, "
+                   "compressed blob) overlap on three CUDA streams" % args.piece_mib)
 
-        def e2e_step():
-            nonlocal d2h
-            dbuf.copy_(host_in, non_blocking=True)
-            r = run(dbuf)
-            nb = r.blob.numel()
-            if nb > host_out["blob"].numel():
-                host_out["blob"] = torch.empty(nb + (nb >> 3), dtype=torch.uint8, pin_memory=True)
-            host_out["cuts"][:r.n_chunks].copy_(r.cuts, non_blocking=True)
-            host_out["digests"][:r.n_chunks * 32].copy_(r.digests.view(-1), non_blocking=True)
-            host_out["canon"][:r.n_chunks].copy_(r.canon, non_blocking=True)
-            host_out["offsets"][:r.offsets.numel()].copy_(r.offsets, non_blocking=True)
-            host_out["blob"][:nb].copy_(r.blob, non_blocking=True)
-            d2h = r.n_chunks * (8 + 32 + 8) + r.offsets.numel() * 8 + nb
-            torch.cuda.synchronize()
+            def e2e_step():
+                nonlocal d2h
+                r = stream_pipe.run(host_in, host_blob_cap=n_avail // 2 + (1 << 20))
+                d2h = r.d2h_bytes
+        else:
+            dbuf = ctx.empty(n_avail + 64, torch.uint8)[:n_avail]
+            cap_chunks = n_avail // cfg.min_size + 2
+            host_out = {"cuts": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
+                        "digests": torch.empty(cap_chunks * 32, dtype=torch.uint8, pin_memory=True),
+                        "canon": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
+                        "offsets": torch.empty(cap_chunks + 1, dtype=torch.int64, pin_memory=True),
+                        "blob": torch.empty(n_avail // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)}
+            api = ("hmse_b200.ShardedIngest.run on a device buffer filled from pinned host memory each step; cuts, digests, "
+                   "canon, offsets and the compressed blob copied back to pinned host memory each step")
+
+            def e2e_step():
+                nonlocal d2h
+                dbuf.copy_(host_in, non_blocking=True)
+                r = run(dbuf)
+                nb = r.blob.numel()
+                if nb > host_out["blob"].numel():
+                    host_out["blob"] = torch.empty(nb + (nb >> 3), dtype=torch.uint8, pin_memory=True)
+                host_out["cuts"][:r.n_chunks].copy_(r.cuts, non_blocking=True)
+                host_out["digests"][:r.n_chunks * 32].copy_(r.digests.view(-1), non_blocking=True)
+                host_out["canon"][:r.n_chunks].copy_(r.canon, non_blocking=True)
+                host_out["offsets"][:r.offsets.numel()].copy_(r.offsets, non_blocking=True)
+                host_out["blob"][:nb].copy_(r.blob, non_blocking=True)
+                d2h = r.n_chunks * (8 + 32 + 8) + r.offsets.numel() * 8 + nb
+                torch.cuda.synchronize()
 
         e2e_step()
         barrier()
@@ -351,19 +374,12 @@ def run_ours(args):
         barrier()
         ems = max_over_ranks(a0.elapsed_time(a1)) / k_e2e
         e2e = {"value": total / (ems * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(n_avail)),
-               "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": ems, "steps": k_e2e,
-               "api": "hmse_b200.Ingest.run on a device buffer filled from pinned host memory each step; cuts, digests, "
-                      "canon, offsets and the compressed blob copied back to pinned host memory each step"}
-        del host_in, host_out, dbuf
+               "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": ems, "steps": k_e2e, "api": api}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.cpu_sample_mib)
 
-    uniq_chunks = sum_over_ranks(int(res.select.numel()))
-    tot_chunks = sum_over_ranks(n_chunks)
-    sel_b = sum_over_ranks(sel_bytes)
-    out_b = sum_over_ranks(out_bytes)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",

@@ -46,6 +46,8 @@ SIGNATURES = {
     "hmse_digest": (_I, [_P, _P, _U64, _P, _U64, _P, _P]),
     "hmse_dedup": (_I, [_P, _P, _U64, _P, _P, _P]),
     "hmse_dedup_select": (_I, [_P, _P, _U64, _P, _U64, _PU64, _P]),
+    "hmse_dedup_begin": (_I, [_P, _U64, _P]),
+    "hmse_dedup_append": (_I, [_P, _P, _U64, _U64, _P, _P, _P]),
     "hmse_timing": (_I, [_P, _I]),
     "hmse_timing_ms": (_I, [_P, _I, C.POINTER(C.c_float)]),
     "hmse_launch_count": (_U64, [_P]),

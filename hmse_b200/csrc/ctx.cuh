@@ -55,6 +55,7 @@ struct hmse_ctx {
     uint64_t seg_len, n_seg, seg_cap;
     uint64_t res_n_own;
     int res_eof, res_valid;
+    uint64_t dedup_cap, dedup_n;  // streaming dedup table (hmse_dedup_begin / hmse_dedup_append)
     void* dict_host;  // host copy + checksum of the indexed preset dictionary (deflate.cu)
 };
 

@@ -40,9 +40,10 @@ __device__ __forceinline__ uint64_t slot_of(const Key& k, uint64_t mask) {
     return (h >> 20) & mask;
 }
 
-__global__ void dedup_insert_kernel(const uint8_t* __restrict__ keys, uint64_t stride, uint64_t n,
+// Inserts keys i0 .. n-1 (earlier indices may already be in the table: streaming append).
+__global__ void dedup_insert_kernel(const uint8_t* __restrict__ keys, uint64_t stride, uint64_t i0, uint64_t n,
                                     uint32_t* __restrict__ table, uint64_t mask) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Key me = load_key(keys, stride, i);
     uint64_t pos = slot_of(me, mask);
@@ -60,19 +61,20 @@ __global__ void dedup_insert_kernel(const uint8_t* __restrict__ keys, uint64_t s
     }
 }
 
-__global__ void dedup_lookup_kernel(const uint8_t* __restrict__ keys, uint64_t stride, uint64_t n,
+// Looks up keys i0 .. n-1; outputs are indexed from i0 (canon[i - i0] holds the absolute index).
+__global__ void dedup_lookup_kernel(const uint8_t* __restrict__ keys, uint64_t stride, uint64_t i0, uint64_t n,
                                     const uint32_t* __restrict__ table, uint64_t mask, int64_t* __restrict__ canon,
                                     uint8_t* __restrict__ is_first, uint64_t* __restrict__ canon_gid) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t i = i0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Key me = load_key(keys, stride, i);
     uint64_t pos = slot_of(me, mask);
     for (;;) {
         uint32_t cur = table[pos];
         if (cur != EMPTY && same(load_key(keys, stride, cur), me)) {
-            if (canon) canon[i] = (int64_t)cur;
-            if (is_first) is_first[i] = cur == (uint32_t)i;
-            if (canon_gid) canon_gid[i] = *reinterpret_cast<const uint64_t*>(keys + (uint64_t)cur * stride + 32);
+            if (canon) canon[i - i0] = (int64_t)cur;
+            if (is_first) is_first[i - i0] = cur == (uint32_t)i;
+            if (canon_gid) canon_gid[i - i0] = *reinterpret_cast<const uint64_t*>(keys + (uint64_t)cur * stride + 32);
             return;
         }
         pos = (pos + 1) & mask;
@@ -86,12 +88,13 @@ int run_table(hmse_ctx* ctx, const uint8_t* keys, uint64_t stride, uint64_t n, i
     while (cap < 2 * n) cap <<= 1;
     HMSE_SCRATCH(ctx, table, uint32_t*, SLOT_DEDUP_TABLE, cap * sizeof(uint32_t));
     HMSE_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t), st));
+    ctx->dedup_cap = 0;   // the one-shot table replaces a streaming one
     const unsigned grid = (unsigned)div_up64(n, 256);
     HT_BEGIN(ctx, HT_DEDUP, st);
     KL(ctx);
-    dedup_insert_kernel<<<grid, 256, 0, st>>>(keys, stride, n, table, cap - 1);
+    dedup_insert_kernel<<<grid, 256, 0, st>>>(keys, stride, 0, n, table, cap - 1);
     KL(ctx);
-    dedup_lookup_kernel<<<grid, 256, 0, st>>>(keys, stride, n, table, cap - 1, canon, is_first, canon_gid);
+    dedup_lookup_kernel<<<grid, 256, 0, st>>>(keys, stride, 0, n, table, cap - 1, canon, is_first, canon_gid);
     HMSE_LAUNCH_CHECK(ctx);
     HT_END(ctx, HT_DEDUP, st);
     return HMSE_OK;
@@ -228,6 +231,45 @@ HMSE_API int hmse_dedup(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, int
     return run_table(ctx, d_digests, 32, n, d_canon, d_is_first, nullptr, (cudaStream_t)stream);
 }
 
+HMSE_API int hmse_dedup_begin(hmse_ctx* ctx, uint64_t max_chunks, void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    if (max_chunks >= 0x7FFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "dedup: more than 2^31-1 chunks per table");
+    uint64_t cap = 1024;
+    while (cap < 2 * max_chunks) cap <<= 1;
+    HMSE_SCRATCH(ctx, table, uint32_t*, SLOT_DEDUP_TABLE, cap * sizeof(uint32_t));
+    HMSE_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t), (cudaStream_t)stream));
+    ctx->dedup_cap = cap;
+    ctx->dedup_n = 0;
+    return HMSE_OK;
+}
+
+HMSE_API int hmse_dedup_append(hmse_ctx* ctx, const uint8_t* d_digests_all, uint64_t n_prev, uint64_t n_new,
+                                 int64_t* d_canon, uint8_t* d_is_first, void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->dedup_cap) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_append: call hmse_dedup_begin first");
+    if (n_prev != ctx->dedup_n) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_append: n_prev %llu != %llu chunks appended so far",
+                                          (unsigned long long)n_prev, (unsigned long long)ctx->dedup_n);
+    if (2 * (n_prev + n_new) > ctx->dedup_cap)
+        HMSE_FAIL(ctx, HMSE_E_CAPACITY, "hmse_dedup_append: table sized for %llu chunks", (unsigned long long)(ctx->dedup_cap / 2));
+    if (n_new == 0) return HMSE_OK;
+    if (!d_digests_all || !d_canon) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_append: null pointer");
+    if ((uintptr_t)d_digests_all & 7) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_digests_all must be 8-byte aligned");
+    uint32_t* table = (uint32_t*)ctx->slot[SLOT_DEDUP_TABLE];
+    const unsigned grid = (unsigned)div_up64(n_new, 256);
+    const uint64_t n = n_prev + n_new;
+    HT_BEGIN(ctx, HT_DEDUP, st);
+    KL(ctx);
+    dedup_insert_kernel<<<grid, 256, 0, st>>>(d_digests_all, 32, n_prev, n, table, ctx->dedup_cap - 1);
+    KL(ctx);
+    dedup_lookup_kernel<<<grid, 256, 0, st>>>(d_digests_all, 32, n_prev, n, table, ctx->dedup_cap - 1, d_canon, d_is_first,
+                                              nullptr);
+    HMSE_LAUNCH_CHECK(ctx);
+    HT_END(ctx, HT_DEDUP, st);
+    ctx->dedup_n = n;
+    return HMSE_OK;
+}
+
 HMSE_API int hmse_dedup_partition(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, uint64_t id_base,
                                     uint32_t world, uint8_t* d_records, uint32_t* d_perm, uint64_t* counts,
                                     void* stream) {
@@ -274,7 +316,7 @@ HMSE_API int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_
     const unsigned grid = (unsigned)div_up64(m, 256);
     HT_BEGIN(ctx, HT_DEDUP, st);
     KL(ctx);
-    dedup_insert_kernel<<<grid, 256, 0, st>>>(d_records, 40, m, table, cap - 1);
+    dedup_insert_kernel<<<grid, 256, 0, st>>>(d_records, 40, 0, m, table, cap - 1);
     KL(ctx);
     min_gid_kernel<<<grid, 256, 0, st>>>(d_records, m, table, cap - 1, min_gid);
     KL(ctx);

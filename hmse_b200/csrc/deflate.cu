@@ -37,6 +37,7 @@ constexpr int DICT_HASH_BITS = 15; // the dictionary index lives in global memor
 constexpr uint32_t DICT_BUCKETS = 1u << DICT_HASH_BITS;
 constexpr uint32_t DICT_MAX = 32768;
 constexpr uint32_t NMAX_SMALL = 12288, NMAX_LARGE = 32768;
+static_assert(NMAX_LARGE / 512 <= 64, "P3b keeps one moved-bit per element of a thread");
 constexpr int T_PARSE = 512;
 constexpr int TILE_SHIFT = 9;       // log2(T_PARSE): a scatter tile is T_PARSE consecutive positions
 static_assert((1 << TILE_SHIFT) == T_PARSE, "TILE_SHIFT");
@@ -333,38 +334,46 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             PROF(3)
             // Buckets are already ordered except for same-hash positions that were scattered in the same
             // tile (common in text: a word repeated within 512 bytes).  Such a group is contiguous in the
-            // bucket; every element finds its rank inside its group (groups are tiny) and is rewritten
-            // in place through a temporary copy.
+            // bucket.  Most elements see at once that neither neighbour comes from their tile; the members
+            // of a group find their rank inside it (groups are tiny; a neighbour belongs to the same
+            // bucket iff its four bytes hash alike) and are rewritten through a temporary copy.
             uint16_t* s_tmp16 = reinterpret_cast<uint16_t*>(mptr);   // match words are not written before P4
-            for (uint32_t i = t; i < (nmax >> 5); i += T) s_flag[i] = 0;   // bit i: sorted index i starts a bucket
-            __syncthreads();
-            for (uint32_t i = 0; i < per; i++) {
-                const uint32_t h = t * per + i;
-                const uint32_t b0 = s_E[h];
-                if (s_E[h + 1] > b0) atomicOr(&s_flag[b0 >> 5], 1u << (b0 & 31));
+            uint64_t moved = 0;   // bit k: this thread's k-th element (index t + k*T) moved; nmax / T <= 64
+            {
+                uint32_t k = 0;
+                for (uint32_t i = t; i < nh; i += T, k++) {
+                    const uint32_t p = s_sorted[i];
+                    const uint32_t tile = p >> TILE_SHIFT;
+                    const uint32_t ql = i ? s_sorted[i - 1] : 0xffffffffu, qr = i + 1 < nh ? s_sorted[i + 1] : 0xffffffffu;
+                    if ((ql >> TILE_SHIFT) != tile && (qr >> TILE_SHIFT) != tile) continue;
+                    const uint32_t h = hash4(ld32u(s_data32, p));
+                    uint32_t first = i, smaller = 0, others = 0;
+                    for (uint32_t j = i; j > 0;) {   // left neighbours of the same tile and bucket
+                        j--;
+                        const uint32_t q = s_sorted[j];
+                        if ((q >> TILE_SHIFT) != tile || hash4(ld32u(s_data32, q)) != h) break;
+                        first = j;
+                        smaller += q < p;
+                        others++;
+                    }
+                    for (uint32_t j = i + 1; j < nh; j++) {
+                        const uint32_t q = s_sorted[j];
+                        if ((q >> TILE_SHIFT) != tile || hash4(ld32u(s_data32, q)) != h) break;
+                        smaller += q < p;
+                        others++;
+                    }
+                    if (others) {
+                        s_tmp16[first + smaller] = (uint16_t)p;
+                        moved |= 1ull << k;
+                    }
+                }
             }
             __syncthreads();
-            for (uint32_t i = t; i < nh; i += T) {
-                const uint32_t p = s_sorted[i];
-                const uint32_t tile = p >> TILE_SHIFT;
-                uint32_t first = i, smaller = 0;
-                // left neighbours of the same bucket and tile
-                for (uint32_t j = i; j > 0 && !((s_flag[j >> 5] >> (j & 31)) & 1u);) {
-                    j--;
-                    const uint32_t q = s_sorted[j];
-                    if ((q >> TILE_SHIFT) != tile) break;
-                    first = j;
-                    smaller += q < p;
-                }
-                for (uint32_t j = i + 1; j < nh && !((s_flag[j >> 5] >> (j & 31)) & 1u); j++) {
-                    const uint32_t q = s_sorted[j];
-                    if ((q >> TILE_SHIFT) != tile) break;
-                    smaller += q < p;
-                }
-                s_tmp16[first + smaller] = (uint16_t)p;
+            // every member of a group wrote one slot of the group's range, so the range is fully defined
+            for (uint64_t m = moved; m; m &= m - 1) {
+                const uint32_t i = t + (uint32_t)(__ffsll((long long)m) - 1) * T;
+                s_sorted[i] = s_tmp16[i];
             }
-            __syncthreads();
-            for (uint32_t i = t; i < nh; i += T) s_sorted[i] = s_tmp16[i];
             __syncthreads();
             PROF(4)
             // ---- P4: matches as RUNS.  A pair (position p, source q) whose four bytes agree and whose
@@ -462,11 +471,13 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                             if ((mask >> sl) & 1u) plist[o++] = rec[sl];
                         pcnt += __shfl_sync(0xffffffffu, inc, 31);
                         __syncwarp();
+                        const long long tb0 = clock64();
                         while (pcnt >= 32) {
                             pcnt -= 32;
                             extend_pairs(pcnt, 32);
                         }
                         __syncwarp();
+                        if (t == 0) atomicAdd(&g_prof[10], (unsigned long long)(clock64() - tb0));
                     }
                 }
                 if (pcnt) extend_pairs(0, pcnt);

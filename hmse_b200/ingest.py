@@ -57,6 +57,148 @@ class Ingest:
         return IngestResult(cuts, digests, canon, first, sel, blob, offs)
 
 
+@dataclass
+class HostIngestResult:
+    """What IngestStream leaves in (pinned) host memory; same meaning as IngestResult, absolute offsets."""
+    cuts: torch.Tensor        # int64 [n]
+    digests: torch.Tensor     # uint8 [n, 32]
+    canon: torch.Tensor       # int64 [n]
+    offsets: torch.Tensor     # int64 [m + 1]
+    blob: torch.Tensor        # uint8
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+    @property
+    def n_chunks(self) -> int:
+        return int(self.cuts.numel())
+
+    @property
+    def is_first(self) -> torch.Tensor:
+        return self.canon == torch.arange(self.canon.numel(), dtype=torch.int64)
+
+    @property
+    def select(self) -> torch.Tensor:
+        return torch.nonzero(self.is_first).view(-1)
+
+
+class IngestStream(Ingest):
+    """Host-to-host ingest of one stream in pieces (the spec's Core 0 I/O stage feeding the
+    pipeline, README.md:141-145): piece k+1 is copied host->device while piece k is chunked,
+    hashed, deduplicated against everything seen so far (hmse_dedup_begin/append) and
+    compressed, and the results of piece k-1 travel device->host - three CUDA streams.
+    A chunk that straddles a piece boundary is resolved with the next piece (the boundary rule of
+    hmse_chunk_resolve), so cuts, digests, canon and streams equal the one-shot `Ingest.run`."""
+
+    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, piece_bytes: int = 256 << 20):
+        super().__init__(ctx, cdc, zdict, level)
+        if piece_bytes % 16 or piece_bytes < 4 * cdc.max_size:
+            raise ValueError("piece_bytes must be a multiple of 16 and >= 4 * max_size")
+        self.piece = int(piece_bytes)
+        self.s_h2d = torch.cuda.Stream(ctx.tdev)
+        self.s_d2h = torch.cuda.Stream(ctx.tdev)
+        self._dbuf = None
+        self._dig = None
+        self._host = None
+
+    def _buffers(self, n: int, host_blob_cap: int):
+        cap_chunks = n // self.cdc.min_size + 2
+        if self._dbuf is None or self._dbuf.numel() < n + 64:
+            self._dbuf = self.ctx.empty(n + 64, torch.uint8)
+        if self._dig is None or self._dig.numel() < cap_chunks * 32:
+            self._dig = self.ctx.empty(cap_chunks * 32, torch.uint8)
+        h = self._host
+        if h is None or h["cuts"].numel() < cap_chunks or h["blob"].numel() < host_blob_cap:
+            h = self._host = {
+                "cuts": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
+                "digests": torch.empty(cap_chunks * 32, dtype=torch.uint8, pin_memory=True),
+                "canon": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
+                "offsets": torch.empty(cap_chunks + 1, dtype=torch.int64, pin_memory=True),
+                "blob": torch.empty(host_blob_cap, dtype=torch.uint8, pin_memory=True)}
+        return cap_chunks, h
+
+    def run(self, host_in: torch.Tensor, host_blob_cap: Optional[int] = None, compress: bool = True) -> HostIngestResult:
+        ctx, cfg = self.ctx, self.cdc
+        if host_in.is_cuda or host_in.dtype != torch.uint8 or host_in.dim() != 1:
+            raise TypeError("host_in must be a 1-D uint8 host tensor (pinned for asynchronous copies)")
+        n = host_in.numel()
+        if host_blob_cap is None:
+            host_blob_cap = n + n // 64 + (1 << 20)
+        cap_chunks, host = self._buffers(n, host_blob_cap)
+        dbuf, dig = self._dbuf, self._dig
+        cur = torch.cuda.current_stream(ctx.device)
+        n_pieces = max(1, (n + self.piece - 1) // self.piece)
+        # every host->device copy is queued up front: the copy engine runs ahead of the kernels
+        self.s_h2d.wait_stream(cur)
+        ev_in = []
+        with torch.cuda.stream(self.s_h2d):
+            for k in range(n_pieces):
+                a, b = k * self.piece, min(n, (k + 1) * self.piece)
+                dbuf[a:b].copy_(host_in[a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.s_h2d)
+                ev_in.append(e)
+        ctx.check(ctx.lib.hmse_dedup_begin(ctx.h, cap_chunks, ctx.stream))
+        host["offsets"][0] = 0
+        keep = []                      # device results stay referenced until the copies out have run
+        entry = 0                      # absolute offset of the first chunk not yet cut
+        n_chunks = m_total = blob_total = 0
+        d2h = 0
+        for k in range(n_pieces):
+            cur.wait_event(ev_in[k])
+            end = min(n, (k + 1) * self.piece)
+            eof = k == n_pieces - 1
+            base = entry & ~15
+            view = dbuf[base:end]
+            n_own = end - base if eof else end - base - cfg.max_size
+            if n_own <= entry - base:
+                continue               # (only when a piece is tiny) nothing can be decided yet
+            ctx.chunk_scan(view, cfg)
+            cuts, exit_off = ctx.chunk_resolve(view, cfg, n_own, eof, entry - base)
+            nk = cuts.numel()
+            if nk == 0:
+                continue
+            dg = dig[n_chunks * 32:(n_chunks + nk) * 32]
+            ctx.check(ctx.lib.hmse_digest(ctx.h, view.data_ptr(), entry - base, cuts.data_ptr(), nk, dg.data_ptr(), ctx.stream))
+            canon = ctx.empty(nk, torch.int64)
+            first = ctx.empty(nk, torch.uint8)
+            ctx.check(ctx.lib.hmse_dedup_append(ctx.h, dig.data_ptr(), n_chunks, nk, canon.data_ptr(), first.data_ptr(),
+                                                ctx.stream))
+            if compress:
+                sel = self.select_first(first)
+                blob, offs = ctx.compress(view, cuts, sel, self.zdict, self.level, start0=entry - base)
+                mk, bk = sel.numel(), blob.numel()
+                if blob_total + bk > host["blob"].numel():
+                    raise ValueError("host_blob_cap %d is too small" % host["blob"].numel())
+                offs_abs = offs[1:] + blob_total
+            else:
+                mk = bk = 0
+            cuts_abs = cuts + base
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.s_d2h.wait_event(ev)
+            with torch.cuda.stream(self.s_d2h):
+                host["cuts"][n_chunks:n_chunks + nk].copy_(cuts_abs, non_blocking=True)
+                host["digests"][n_chunks * 32:(n_chunks + nk) * 32].copy_(dg, non_blocking=True)
+                host["canon"][n_chunks:n_chunks + nk].copy_(canon, non_blocking=True)
+                d2h += nk * 48
+                if mk:
+                    host["offsets"][1 + m_total:1 + m_total + mk].copy_(offs_abs, non_blocking=True)
+                    host["blob"][blob_total:blob_total + bk].copy_(blob, non_blocking=True)
+                    d2h += mk * 8 + bk
+                    keep += [offs_abs, blob]
+            keep += [cuts_abs, canon]
+            n_chunks += nk
+            m_total += mk
+            blob_total += bk
+            entry = base + exit_off
+        cur.wait_stream(self.s_d2h)    # the caller's stream (and its events) see the whole job
+        torch.cuda.current_stream(ctx.device).synchronize()
+        del keep
+        return HostIngestResult(host["cuts"][:n_chunks], host["digests"][:n_chunks * 32].view(n_chunks, 32),
+                                host["canon"][:n_chunks], host["offsets"][:m_total + 1], host["blob"][:blob_total],
+                                h2d_bytes=n, d2h_bytes=d2h)
+
+
 class ShardedIngest(Ingest):
     """Rank r holds stream bytes [lo_r, hi_r + max_size) (the last rank up to the stream end).
     Chunks are owned by the shard they start in; global ids follow stream order."""

@@ -111,6 +111,17 @@ int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uin
 int hmse_dedup(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, int64_t* d_canon,
                uint8_t* d_is_first, void* stream);
 
+/* Streaming form of hmse_dedup over one growing digest array (the ChunkIndex insert rule applied
+ * piece by piece, README.md:1542-1551).  hmse_dedup_begin sizes and clears the table for up to
+ * max_chunks chunks; hmse_dedup_append inserts chunks [n_prev, n_prev + n_new) of d_digests_all
+ * (whose first n_prev rows must be the ones appended so far, at the same address) and writes
+ * d_canon[i - n_prev] = smallest j <= i with digest j == digest i (absolute indices),
+ * d_is_first[i - n_prev] = (canon == i).  Results equal hmse_dedup over the whole array.
+ * hmse_dedup and hmse_dedup_records use the same table: one table per ctx at a time. */
+int hmse_dedup_begin(hmse_ctx* ctx, uint64_t max_chunks, void* stream);
+int hmse_dedup_append(hmse_ctx* ctx, const uint8_t* d_digests_all, uint64_t n_prev, uint64_t n_new,
+                      int64_t* d_canon, uint8_t* d_is_first, void* stream);
+
 /* d_select[0..*m) = ascending indices i with d_is_first[i] != 0 (the chunks to store/compress).
  * On HMSE_E_CAPACITY *m holds the required capacity. */
 int hmse_dedup_select(hmse_ctx* ctx, const uint8_t* d_is_first, uint64_t n, uint64_t* d_select, uint64_t cap,
