@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gb", type=float, default=10.0, help="bytes per GPU per step, in GB (1e9)")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
-    ap.add_argument("--piece-mib", type=int, default=256, help="piece size of the streaming end-to-end path")
+    ap.add_argument("--piece-mib", type=int, default=1024, help="piece size of the streaming end-to-end path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

@@ -156,25 +156,27 @@ class Context:
 
     # -- L1 -------------------------------------------------------------------------------
     def compress(self, d: torch.Tensor, cuts: torch.Tensor, select: Optional[torch.Tensor], zdict: Optional[torch.Tensor],
-                 level: int = 6, start0: int = 0, out_cap: Optional[int] = None):
+                 level: int = 6, start0: int = 0, out_cap: Optional[int] = None, out: Optional[torch.Tensor] = None):
+        """(blob, offsets).  `out` (uint8 device tensor) receives the blob when it is large enough; otherwise a
+        tensor of the required size is allocated (input bytes + per-chunk slack bounds any stream)."""
         m = cuts.numel() if select is None else select.numel()
         offsets = self.empty(m + 1, torch.int64)
-        if out_cap is None:
-            # a dynamic block never beats stored by more than the input size: input bytes + per-chunk slack
-            span = int(d.numel())
-            out_cap = span + 64 * m + 1024 if select is None else None
-        if out_cap is None:
+        if out is not None:
+            out_cap = out.numel()
+        elif out_cap is None:
             out_cap = int(d.numel()) + 64 * m + 1024
         total = C.c_uint64(0)
         zp = zdict.data_ptr() if zdict is not None and zdict.numel() else None
         zl = zdict.numel() if zdict is not None else 0
         sp = select.data_ptr() if select is not None else None
         for _ in range(2):
-            out = self.empty(out_cap, torch.uint8)
+            if out is None:
+                out = self.empty(out_cap, torch.uint8)
             rc = self.lib.hmse_compress(self.h, d.data_ptr(), start0, cuts.data_ptr(), sp, m, zp, zl, level,
                                         out.data_ptr(), out_cap, offsets.data_ptr(), C.byref(total), self.stream)
             if rc == _lib.HMSE_E_CAPACITY and total.value > out_cap:
                 out_cap = int(total.value)
+                out = None
                 continue
             self.check(rc)
             return out[:total.value], offsets

@@ -517,7 +517,7 @@ HMSE_API int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n
         KL(ctx);
         resolve_fix_kernel<<<wgrid, K2_THREADS, 0, st>>>(a, in, (uint32_t*)tail);
         HMSE_LAUNCH_CHECK(ctx);
-        HMSE_CUDA(ctx, cudaMemcpyAsync((void*)mail, tail, 8, cudaMemcpyDeviceToHost, st));
+        if (int mrc = hmse_mail(ctx, 0, tail, 2, st)) return mrc;
         HMSE_CUDA(ctx, cudaStreamSynchronize(st));
         in ^= 1;
         rounds++;
@@ -543,8 +543,8 @@ HMSE_API int hmse_chunk_resolve(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n
         HMSE_LAUNCH_CHECK(ctx);
     }
     HT_END(ctx, HT_RESOLVE, st);
-    HMSE_CUDA(ctx, cudaMemcpyAsync((void*)mail, tail + 1, 8, cudaMemcpyDeviceToHost, st));
-    HMSE_CUDA(ctx, cudaMemcpyAsync((void*)(mail + 1), &meta[n_seg - 1].exit[in], 8, cudaMemcpyDeviceToHost, st));
+    if (int mrc = hmse_mail(ctx, 0, tail + 1, 2, st)) return mrc;
+    if (int mrc = hmse_mail(ctx, 2, &meta[n_seg - 1].exit[in], 2, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     *n_cuts = mail[0];
     if (exit_off) *exit_off = mail[1];

@@ -23,7 +23,8 @@ HMSE_API int hmse_create(int device, hmse_ctx** out) {
         return HMSE_E_CUDA;
     }
     c->sm_count = prop.multiProcessorCount;
-    if (cudaMallocHost((void**)&c->pinned, 4096) != cudaSuccess) {
+    if (cudaHostAlloc((void**)&c->pinned, 4096, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->pinned_dev, c->pinned, 0) != cudaSuccess) {
         delete c;
         return HMSE_E_CUDA;
     }
@@ -83,6 +84,21 @@ void* hmse_scratch(hmse_ctx* ctx, int slot, size_t bytes) {
     ctx->slot[slot] = p;
     ctx->slot_bytes[slot] = want;
     return p;
+}
+
+namespace {
+__global__ void mail_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n32) {
+    for (uint32_t i = threadIdx.x; i < n32; i += blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+int hmse_mail(hmse_ctx* ctx, uint32_t word32, const void* d_src, uint32_t n32, cudaStream_t stream) {
+    if ((size_t)(word32 + n32) * 4 > 4096) HMSE_FAIL(ctx, HMSE_E_INVAL, "mailbox overflow");
+    KL(ctx);
+    mail_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t*>(ctx->pinned_dev) + word32,
+                                      reinterpret_cast<const uint32_t*>(d_src), n32);
+    HMSE_LAUNCH_CHECK(ctx);
+    return HMSE_OK;
 }
 
 HMSE_API int hmse_timing(hmse_ctx* ctx, int enable) {

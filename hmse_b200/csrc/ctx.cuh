@@ -43,7 +43,8 @@ struct hmse_ctx {
     char err[512];
     void* slot[SLOT_COUNT];
     size_t slot_bytes[SLOT_COUNT];
-    uint64_t* pinned;  // small pinned host mailbox (4 KiB)
+    uint64_t* pinned;  // small pinned host mailbox (4 KiB), mapped: kernels write results into it directly
+    uint64_t* pinned_dev;  // its device-side address
     int sm_count;
     // CDC state carried from scan to resolve
     uint64_t cdc_n_avail;
@@ -98,5 +99,11 @@ void* hmse_scratch(hmse_ctx* ctx, int slot, size_t bytes);
 // receives the grand total.  Uses SLOT_SCAN.  Asynchronous on `stream`.
 int hmse_exclusive_scan_u64(hmse_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n,
                             uint64_t* d_total, cudaStream_t stream);
+
+// Small results travel to the host through the mapped mailbox, written by a one-warp kernel: a
+// cudaMemcpyAsync would queue behind whatever bulk copy occupies the device-to-host engine
+// (the compressed blobs of the previous piece, when the caller streams), a store from an SM does not.
+// Copies n32 32-bit words from d_src to mailbox word `word32` (4-byte units).  Asynchronous on `stream`.
+int hmse_mail(hmse_ctx* ctx, uint32_t word32, const void* d_src, uint32_t n32, cudaStream_t stream);
 
 static inline uint64_t div_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

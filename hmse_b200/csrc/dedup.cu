@@ -214,7 +214,7 @@ HMSE_API int hmse_dedup_select(hmse_ctx* ctx, const uint8_t* d_is_first, uint64_
         select_scatter_kernel<<<grid, 256, 0, st>>>(d_is_first, tmp, n, cap, d_select);
         HMSE_LAUNCH_CHECK(ctx);
     }
-    HMSE_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, tmp + n, 8, cudaMemcpyDeviceToHost, st));
+    if (int mrc = hmse_mail(ctx, 0, tmp + n, 2, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     *m = ctx->pinned[0];
     if (!d_select || *m > cap)
@@ -294,7 +294,7 @@ HMSE_API int hmse_dedup_partition(hmse_ctx* ctx, const uint8_t* d_digests, uint6
     owner_scatter_kernel<<<grid, 256, 0, st>>>(d_digests, n, id_base, world, misc + world,
                                                (unsigned long long*)(misc + 2 * world), d_records, d_perm);
     HMSE_LAUNCH_CHECK(ctx);
-    HMSE_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, misc, world * 8, cudaMemcpyDeviceToHost, st));
+    if (int mrc = hmse_mail(ctx, 0, misc, world * 2, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     for (uint32_t w = 0; w < world; w++) counts[w] = ctx->pinned[w];
     return HMSE_OK;

@@ -1096,12 +1096,44 @@ uint32_t host_adler32(const uint8_t* d, size_t n) {
     return (b << 16) | a;
 }
 
+// 128-bit fingerprint of the dictionary bytes (position-dependent mixes, summed), written straight into
+// the mapped mailbox words 0..1: lets hmse_compress recognise the dictionary it has already indexed
+// without copying 32 KiB to the host on every call.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) dict_fingerprint_kernel(const uint8_t* __restrict__ d, uint32_t n, uint64_t* __restrict__ out) {
+    __shared__ uint64_t s0[256], s1[256];
+    uint64_t a = 0, b = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        const uint64_t x = ((uint64_t)i << 8) | d[i];
+        a += mix64(x + 0x9E3779B97F4A7C15ull);
+        b += mix64(x ^ 0xD6E8FEB86659FD93ull);
+    }
+    s0[threadIdx.x] = a;
+    s1[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 256; i++) {
+            a += s0[i];
+            b += s1[i];
+        }
+        out[0] = a;
+        out[1] = b;
+    }
+}
+
 // Dictionary setup (the analogue of zlib's deflateSetDictionary): a <= 32 KiB one-off, indexed on
 // the host and cached until the dictionary bytes change.  Not on the per-chunk path.
 struct DictHost {
     uint8_t bytes[DICT_MAX];
     uint32_t len;
     uint32_t adler;
+    uint64_t fp[2];
     int valid;
 };
 
@@ -1113,13 +1145,20 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
         if (!hd) HMSE_FAIL(ctx, HMSE_E_NOMEM, "dictionary host copy");
         ctx->dict_host = hd;
     }
-    static thread_local uint8_t tmp[DICT_MAX];
-    HMSE_CUDA(ctx, cudaMemcpyAsync(tmp, d_zdict, dict_len, cudaMemcpyDeviceToHost, st));
+    KL(ctx);
+    dict_fingerprint_kernel<<<1, 256, 0, st>>>(d_zdict, dict_len, ctx->pinned_dev);
+    HMSE_LAUNCH_CHECK(ctx);
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
-    if (hd->valid && hd->len == dict_len && memcmp(hd->bytes, tmp, dict_len) == 0) {
+    const uint64_t fp0 = ctx->pinned[0], fp1 = ctx->pinned[1];
+    if (hd->valid && hd->len == dict_len && hd->fp[0] == fp0 && hd->fp[1] == fp1) {
         *adler = hd->adler;
         return HMSE_OK;
     }
+    static thread_local uint8_t tmp[DICT_MAX];
+    HMSE_CUDA(ctx, cudaMemcpyAsync(tmp, d_zdict, dict_len, cudaMemcpyDeviceToHost, st));
+    HMSE_CUDA(ctx, cudaStreamSynchronize(st));
+    hd->fp[0] = fp0;
+    hd->fp[1] = fp1;
     hd->valid = 0;
     memcpy(hd->bytes, tmp, dict_len);
     hd->len = dict_len;
@@ -1208,8 +1247,8 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     int rc = hmse_exclusive_scan_u64(ctx, slot_size, slot_off, m, d_tot, st);
     if (rc) return rc;
     volatile uint64_t* mail = ctx->pinned;
-    HMSE_CUDA(ctx, cudaMemcpyAsync((void*)mail, d_tot, 8, cudaMemcpyDeviceToHost, st));
-    HMSE_CUDA(ctx, cudaMemcpyAsync((void*)(mail + 1), list_n, 16, cudaMemcpyDeviceToHost, st));
+    if (int mrc = hmse_mail(ctx, 0, d_tot, 2, st)) return mrc;
+    if (int mrc = hmse_mail(ctx, 2, list_n, 4, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t stage_bytes = mail[0];
     const uint32_t* hn = (const uint32_t*)(mail + 1);
@@ -1293,7 +1332,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     HMSE_CUDA(ctx, cudaMemsetAsync(sizes + m, 0, 8, st));
     rc = hmse_exclusive_scan_u64(ctx, sizes, d_offsets, m + 1, d_tot + 1, st);
     if (rc) return rc;
-    HMSE_CUDA(ctx, cudaMemcpyAsync((void*)mail, d_tot + 1, 8, cudaMemcpyDeviceToHost, st));
+    if (int mrc = hmse_mail(ctx, 0, d_tot + 1, 2, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     *total = mail[0];
     if (!d_out || mail[0] > out_cap)

@@ -87,9 +87,11 @@ class IngestStream(Ingest):
     hashed, deduplicated against everything seen so far (hmse_dedup_begin/append) and
     compressed, and the results of piece k-1 travel device->host - three CUDA streams.
     A chunk that straddles a piece boundary is resolved with the next piece (the boundary rule of
-    hmse_chunk_resolve), so cuts, digests, canon and streams equal the one-shot `Ingest.run`."""
+    hmse_chunk_resolve), so cuts, digests, canon and streams equal the one-shot `Ingest.run`.
+    Pieces grow from piece_bytes/16 to piece_bytes and shrink again at the end of the stream: the
+    first kernels start after a short copy and little is left to copy out after the last one."""
 
-    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, piece_bytes: int = 256 << 20):
+    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, piece_bytes: int = 1 << 30):
         super().__init__(ctx, cdc, zdict, level)
         if piece_bytes % 16 or piece_bytes < 4 * cdc.max_size:
             raise ValueError("piece_bytes must be a multiple of 16 and >= 4 * max_size")
@@ -99,10 +101,44 @@ class IngestStream(Ingest):
         self._dbuf = None
         self._dig = None
         self._host = None
+        self._stage = [None, None]   # device blobs of the pieces in flight (double buffer)
+        self.trace = None   # set to a list to collect (label, host ms since run() began) marks
+        self.timing_hook = None   # called once per piece after its kernels are queued (bench: per-stage event spans)
+
+    def schedule(self, n: int):
+        """Piece end offsets: sizes ramp x4 from piece/16 up to piece, and down again at the end."""
+        lo = max(4 * self.cdc.max_size, (self.piece // 16) & ~15)
+        up, s = [], lo
+        while s < self.piece:
+            up.append(s)
+            s *= 4
+        if n <= 2 * sum(up) + self.piece:   # short stream: equal pieces
+            k = max(1, -(-n // self.piece))
+            step = (-(-n // k) + 15) & ~15
+            return [min(n, (i + 1) * step) for i in range(k)]
+        ends, pos = [], 0
+        for s in up:
+            pos += s
+            ends.append(pos)
+        tail = sum(up)
+        while n - tail - pos > self.piece:
+            pos += self.piece
+            ends.append(pos)
+        rest = n - tail - pos
+        if rest > 0:
+            pos += (rest + 15) & ~15 if rest % 16 and pos + ((rest + 15) & ~15) <= n - tail else rest & ~15
+            if pos > ends[-1]:
+                ends.append(pos)
+        for s in reversed(up):
+            pos = n if s == up[0] else min(n, pos + s)
+            ends.append(pos)
+        ends[-1] = n
+        return [e for i, e in enumerate(ends) if i == 0 or e > ends[i - 1]]
 
     def _buffers(self, n: int, host_blob_cap: int):
         cap_chunks = n // self.cdc.min_size + 2
         if self._dbuf is None or self._dbuf.numel() < n + 64:
+            self._dbuf = None
             self._dbuf = self.ctx.empty(n + 64, torch.uint8)
         if self._dig is None or self._dig.numel() < cap_chunks * 32:
             self._dig = self.ctx.empty(cap_chunks * 32, torch.uint8)
@@ -117,43 +153,54 @@ class IngestStream(Ingest):
         return cap_chunks, h
 
     def run(self, host_in: torch.Tensor, host_blob_cap: Optional[int] = None, compress: bool = True) -> HostIngestResult:
+        import time
         ctx, cfg = self.ctx, self.cdc
         if host_in.is_cuda or host_in.dtype != torch.uint8 or host_in.dim() != 1:
             raise TypeError("host_in must be a 1-D uint8 host tensor (pinned for asynchronous copies)")
         n = host_in.numel()
+        t_run = time.perf_counter()
+
+        def mark(label):
+            if self.trace is not None:
+                self.trace.append((label, (time.perf_counter() - t_run) * 1e3))
         if host_blob_cap is None:
             host_blob_cap = n + n // 64 + (1 << 20)
         cap_chunks, host = self._buffers(n, host_blob_cap)
         dbuf, dig = self._dbuf, self._dig
         cur = torch.cuda.current_stream(ctx.device)
-        n_pieces = max(1, (n + self.piece - 1) // self.piece)
+        ends = self.schedule(n) if n else [0]
         # every host->device copy is queued up front: the copy engine runs ahead of the kernels
         self.s_h2d.wait_stream(cur)
         ev_in = []
         with torch.cuda.stream(self.s_h2d):
-            for k in range(n_pieces):
-                a, b = k * self.piece, min(n, (k + 1) * self.piece)
-                dbuf[a:b].copy_(host_in[a:b], non_blocking=True)
+            a = 0
+            for b in ends:
+                if b > a:
+                    dbuf[a:b].copy_(host_in[a:b], non_blocking=True)
                 e = torch.cuda.Event()
                 e.record(self.s_h2d)
                 ev_in.append(e)
+                a = b
+        mark("copies queued")
         ctx.check(ctx.lib.hmse_dedup_begin(ctx.h, cap_chunks, ctx.stream))
         host["offsets"][0] = 0
-        keep = []                      # device results stay referenced until the copies out have run
+        keep = []                      # small device results stay referenced until the copies out have run
+        ev_out = [None, None]          # copy-out of the piece that last used stage buffer j
         entry = 0                      # absolute offset of the first chunk not yet cut
         n_chunks = m_total = blob_total = 0
         d2h = 0
-        for k in range(n_pieces):
+        for k, end in enumerate(ends):
             cur.wait_event(ev_in[k])
-            end = min(n, (k + 1) * self.piece)
-            eof = k == n_pieces - 1
+            eof = k == len(ends) - 1
             base = entry & ~15
             view = dbuf[base:end]
             n_own = end - base if eof else end - base - cfg.max_size
             if n_own <= entry - base:
                 continue               # (only when a piece is tiny) nothing can be decided yet
+            mark("piece %d start" % k)
             ctx.chunk_scan(view, cfg)
             cuts, exit_off = ctx.chunk_resolve(view, cfg, n_own, eof, entry - base)
+            mark("piece %d cuts" % k)
             nk = cuts.numel()
             if nk == 0:
                 continue
@@ -163,15 +210,24 @@ class IngestStream(Ingest):
             first = ctx.empty(nk, torch.uint8)
             ctx.check(ctx.lib.hmse_dedup_append(ctx.h, dig.data_ptr(), n_chunks, nk, canon.data_ptr(), first.data_ptr(),
                                                 ctx.stream))
+            mk = bk = 0
             if compress:
                 sel = self.select_first(first)
-                blob, offs = ctx.compress(view, cuts, sel, self.zdict, self.level, start0=entry - base)
+                mark("piece %d dedup" % k)
+                j = k & 1
+                want = (end - base) // 2 + (1 << 20)
+                if self._stage[j] is None or self._stage[j].numel() < want:
+                    self._stage[j] = None
+                    self._stage[j] = ctx.empty(want, torch.uint8)
+                if ev_out[j] is not None:
+                    cur.wait_event(ev_out[j])      # the buffer's previous contents have left the device
+                blob, offs = ctx.compress(view, cuts, sel, self.zdict, self.level, start0=entry - base, out=self._stage[j])
+                if blob.data_ptr() != self._stage[j].data_ptr():   # did not fit (poorly compressible piece): keep the larger one
+                    self._stage[j] = blob
                 mk, bk = sel.numel(), blob.numel()
                 if blob_total + bk > host["blob"].numel():
                     raise ValueError("host_blob_cap %d is too small" % host["blob"].numel())
                 offs_abs = offs[1:] + blob_total
-            else:
-                mk = bk = 0
             cuts_abs = cuts + base
             ev = torch.cuda.Event()
             ev.record(cur)
@@ -185,14 +241,21 @@ class IngestStream(Ingest):
                     host["offsets"][1 + m_total:1 + m_total + mk].copy_(offs_abs, non_blocking=True)
                     host["blob"][blob_total:blob_total + bk].copy_(blob, non_blocking=True)
                     d2h += mk * 8 + bk
-                    keep += [offs_abs, blob]
+                    keep.append(offs_abs)
+                    ev_out[k & 1] = torch.cuda.Event()
+                    ev_out[k & 1].record(self.s_d2h)
             keep += [cuts_abs, canon]
+            if self.timing_hook is not None:
+                torch.cuda.current_stream(ctx.device).synchronize()
+                self.timing_hook()
             n_chunks += nk
             m_total += mk
             blob_total += bk
             entry = base + exit_off
+        mark("last piece queued")
         cur.wait_stream(self.s_d2h)    # the caller's stream (and its events) see the whole job
         torch.cuda.current_stream(ctx.device).synchronize()
+        mark("done")
         del keep
         return HostIngestResult(host["cuts"][:n_chunks], host["digests"][:n_chunks * 32].view(n_chunks, 32),
                                 host["canon"][:n_chunks], host["offsets"][:m_total + 1], host["blob"][:blob_total],

@@ -16,7 +16,7 @@ def _one_shot(ctx, data, zd):
     return r
 
 
-@pytest.mark.parametrize("piece_kib", [128, 1024, 3000 * 16 // 16, 1 << 14])
+@pytest.mark.parametrize("piece_kib", [128, 1024, 3000, 1 << 14])
 def test_stream_equals_one_shot_and_oracle(ctx, corpus8, piece_kib):
     import torch
     import hmse_b200
