@@ -264,6 +264,11 @@ def compress(data, cuts, select, zdict: bytes = b"", level: int = 6, start0: int
     return (blob, offs) if dev else (blob.cpu().numpy(), _np_u64(offs))
 
 
+def compress_bound(n: int) -> int:
+    """Worst-case bytes of one zlib stream for a chunk of n bytes (hmse_compress_bound)."""
+    return int(_lib.load().hmse_compress_bound(int(n)))
+
+
 def similarity(data, cuts, cfg: SimConfig = SimConfig(), start0: int = 0, ctx: Optional[Context] = None):
     """(sig uint32[n, n_perm], keys uint64[n, bands], (band u32, key u64, id u64) sorted)."""
     ctx = ctx or default_context()

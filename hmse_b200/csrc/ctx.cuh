@@ -22,6 +22,8 @@ enum HmseSlot {
     SLOT_DEFLATE_MISC,  // sizes, slot offsets, class lists, counters
     SLOT_DEFLATE_DICT,  // hash-sorted index of the preset dictionary
     SLOT_DEFLATE_WORK,  // per-CTA match scratch for the large class
+    SLOT_DEFLATE_LONG,  // block plan of chunks longer than 32 KiB
+    SLOT_DEFLATE_LDICT, // per-block indexes of the previous block (long chunks)
     SLOT_MINHASH_MISC,  // work counter
     SLOT_LSH_SORT,      // radix-sort ping-pong buffers
     SLOT_LSH_MISC,      // digit histograms

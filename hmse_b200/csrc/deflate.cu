@@ -24,6 +24,8 @@
 // Output is compared with zlib by inflate-equality and total size only (never byte for byte).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "ctx.cuh"
 #include "deflate_core.h"
 
@@ -44,6 +46,11 @@ static_assert((1 << TILE_SHIFT) == T_PARSE, "TILE_SHIFT");
 constexpr int T_ENCODE = 256;
 constexpr int HUFF_WARPS = 8;
 constexpr uint32_t BATCH_SMALL = 32768, BATCH_LARGE = 8192;  // chunks per batch (bounds the token scratch)
+// Chunks longer than NMAX_LARGE become one zlib stream of several DEFLATE blocks of LONG_BLOCK input bytes.
+// Block b >= 1 is parsed like any chunk, with the PREVIOUS block of the same chunk in the role of the preset
+// dictionary (indexed on the device), which gives every position zlib's full 32 KiB window.
+constexpr uint32_t LONG_BLOCK = 32768;
+constexpr uint32_t BATCH_LONG = 96;   // blocks per batch: each carries a 0.5 MB dictionary index
 constexpr uint32_t REC_WORDS = 320;                          // 288 lit/len + 32 dist counters / codes
 
 // Device image of the dictionary index (SLOT_DEFLATE_DICT), built on the host once per dictionary.
@@ -64,8 +71,11 @@ struct ChunkRec {
     uint32_t adler;
     uint32_t mode;      // 0 stored, 1 fixed, 2 dynamic
     uint32_t hdr_bits;
-    uint32_t pad[3];
+    uint32_t flags;     // REC_MULTI: one block of a multi-block stream (never stored on its own); REC_LAST: BFINAL
+    uint32_t bits;      // bits of the whole block (header + tokens + end-of-block) in the chosen mode
+    uint32_t pad;
 };
+constexpr uint32_t REC_MULTI = 1, REC_LAST = 2;
 
 struct DeflArgs {
     const uint8_t* data;
@@ -75,7 +85,10 @@ struct DeflArgs {
     const DictDev* dict;
     uint32_t dict_len, dict_adler;
     int level;
-    const uint32_t* list;    // selection slots of this size class
+    const uint32_t* list;    // selection slots of this size class (long class: one entry per BLOCK)
+    const uint32_t* blk;     // long class: block number inside the chunk (null otherwise)
+    const DictDev* long_dicts;  // long class: per batch job, the index of the previous block
+    const uint8_t* stored_flag; // stored_kernel: only the list entries flagged here (null = all)
     uint32_t job0, job1;     // batch = list[job0 .. job1)
     uint32_t nmax;
     int match_smem;          // match words live in shared memory (small class) or in `match`
@@ -250,9 +263,20 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
         const uint32_t bj = job - a.job0;  // index inside the batch
         const uint32_t k = a.list[job];
         const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
-        const uint64_t cs = j ? a.cuts[j - 1] : a.start0;
-        const uint32_t n = (uint32_t)(a.cuts[j] - cs);
+        uint64_t cs = j ? a.cuts[j - 1] : a.start0;
+        uint64_t len = a.cuts[j] - cs;
+        const uint32_t blkno = a.blk ? a.blk[job] : 0u;
+        uint32_t rec_flags = 0;
+        if (a.blk) {   // one block of a long chunk
+            rec_flags = REC_MULTI | ((uint64_t)(blkno + 1) * LONG_BLOCK >= len ? REC_LAST : 0u);
+            cs += (uint64_t)blkno * LONG_BLOCK;
+            len = len - (uint64_t)blkno * LONG_BLOCK < LONG_BLOCK ? len - (uint64_t)blkno * LONG_BLOCK : LONG_BLOCK;
+        }
+        const uint32_t n = (uint32_t)len;
         const uint8_t* src = a.data + cs;
+        // the dictionary of this job: the preset one, or (blocks after the first) the previous block
+        const DictDev* dict = blkno ? a.long_dicts + bj : a.dict;
+        const uint32_t dlen = blkno ? LONG_BLOCK : a.dict_len;
 
         // ---- P0: stage the chunk (byte-unaligned source -> aligned words), clear tables -----
         {
@@ -389,8 +413,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             for (uint32_t i = t; i < n + (n >> 5); i += T) mptr[i] = 0;   // run keys: end << 15 | (32768 - dist)
             __syncthreads();
             {
-                const uint32_t* dictw = reinterpret_cast<const uint32_t*>(a.dict->bytes);
-                const bool use_dict = a.dict_len != 0;
+                const uint32_t* dictw = reinterpret_cast<const uint32_t*>(dict->bytes);
+                const bool use_dict = dlen != 0;
                 uint32_t* plist = s_cnt32 + warp * PAIR_CAP;   // the bucket table is dead: E is not needed to walk s_sorted
                 uint32_t pcnt = 0;                             // warp-uniform
                 const uint32_t nwin = (nh + 27) / 28;
@@ -404,7 +428,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         const uint32_t p = s_sorted[i];
                         r.v = ld32u(s_data32, p);
                         r.pp = p | ((p ? (uint32_t)s_data[p - 1] : CHUNK_PREV0) << 16);
-                        if (use_dict && lane >= 4) r.bk = __ldg(&a.dict->bk4[hash_dict(r.v)]);
+                        if (use_dict && lane >= 4) r.bk = __ldg(&dict->bk4[hash_dict(r.v)]);
                     }
                     return r;
                 };
@@ -416,8 +440,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         uint32_t lim = n - p, dist = p - src;
                         const uint32_t* sw = s_data32;
                         if (isd) {
-                            lim = min(lim, a.dict_len - src);   // matches do not run from the dictionary into the chunk
-                            dist = p + a.dict_len - src;
+                            lim = min(lim, dlen - src);   // matches do not run from the dictionary into the chunk
+                            dist = p + dlen - src;
                             sw = dictw;
                         }
                         const uint32_t l = extend_run(s_data32, sw, p, src, 0, lim);   // from 0: dictionary tags are only a filter
@@ -451,7 +475,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                             const uint32_t x = c[u] ^ my;   // valid, same tag, different previous byte, inside the window
                             const uint32_t j = c[u] & 0x7fffu;
                             if (act && (int32_t)c[u] < 0 && (x & 0x7f800000u) == 0 && (x & 0x007f8000u) != 0 &&
-                                p + a.dict_len - j <= (uint32_t)WSIZE)
+                                p + dlen - j <= (uint32_t)WSIZE)
                                 mask |= 16u << u;
                             rec[OWN_CAP + u] = p | 0x8000u | (j << 16);
                         }
@@ -632,7 +656,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             rec.adler = (sm->adler_b << 16) | sm->adler_a;
             rec.mode = a.level == 0 ? 0u : 2u;
             rec.hdr_bits = 0;
-            rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+            rec.flags = rec_flags;
+            rec.bits = 0;
+            rec.pad = 0;
             a.recs[bj] = rec;
         }
         PROF(8)
@@ -651,7 +677,7 @@ struct HuffSm {
     DynHeader dh;
     uint8_t hdr[640];
     uint32_t bl32[16];
-    uint32_t n_used, cost_dyn, cost_fix, mode, hdr_bits;
+    uint32_t n_used, cost_dyn, cost_fix, mode, hdr_bits, bits;
     unsigned long long kraft;
 };
 
@@ -773,16 +799,19 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
             const uint64_t dyn_bits = (uint64_t)s.dh.bits + s.cost_dyn, fix_bits = 3ull + s.cost_fix;
             uint32_t mode = dyn_bits < fix_bits ? 2u : 1u;
             const uint64_t best_bits = dyn_bits < fix_bits ? dyn_bits : fix_bits;
-            if ((uint64_t)rec.n + 5 <= (best_bits + 7) / 8) mode = 0;
+            const bool multi = (rec.flags & REC_MULTI) != 0;   // stored is decided for the whole stream (encode_long_kernel)
+            if (!multi && (uint64_t)rec.n + 5 <= (best_bits + 7) / 8) mode = 0;
+            const uint32_t bfinal = (!multi || (rec.flags & REC_LAST)) ? 1u : 0u;
             BitWriter bw;
             bw.buf = s.hdr;
             bw.bitpos = 0;
             if (mode == 2) {
-                write_dynamic_header(s.dh, bw, 1);
+                write_dynamic_header(s.dh, bw, (int)bfinal);
             } else if (mode == 1) {
-                bw.put(1, 1);
+                bw.put(bfinal, 1);
                 bw.put(1, 2);
             }
+            s.bits = (uint32_t)best_bits;
             bw.finish();
             s.mode = mode;
             s.hdr_bits = (uint32_t)bw.bitpos;
@@ -803,6 +832,7 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
         if (lane == 0) {
             a.recs[bj].mode = mode;
             a.recs[bj].hdr_bits = s.hdr_bits;
+            a.recs[bj].bits = s.bits;
         }
         __syncwarp();
     }
@@ -859,6 +889,87 @@ __device__ __forceinline__ void word_bits(const uint32_t* codes, uint32_t w, uin
     nb = cl + eb;
 }
 
+// Emits one coded block (mode 1 or 2) of batch job bj at bit offset bit0 of the stream words out32, which the
+// caller has zeroed (words shared by two writers are OR-ed).  Collective over the CTA; returns the bit offset
+// after the end-of-block code.
+__device__ uint32_t emit_block(const DeflArgs& a, uint32_t bj, const ChunkRec& rec, uint32_t* out32, uint32_t bit0,
+                               uint32_t* s_codes, uint32_t* s_tmp, uint32_t* s_hdr) {
+    const uint32_t T = T_ENCODE, t = threadIdx.x;
+    __syncthreads();
+    for (uint32_t i = t; i < REC_WORDS; i += T) s_codes[i] = a.hist[(size_t)bj * REC_WORDS + i];
+    const uint32_t hbytes = (rec.hdr_bits + 7) >> 3;
+    for (uint32_t i = t; i < 160; i += T) s_hdr[i] = 0;
+    __syncthreads();
+    {
+        const uint8_t* gh = a.hdrs + (size_t)bj * 640;
+        uint8_t* sh = reinterpret_cast<uint8_t*>(s_hdr);
+        for (uint32_t i = t; i < hbytes; i += T) sh[i] = gh[i];
+    }
+    const uint16_t* tk = a.tokens + (size_t)bj * a.nmax;
+    const uint32_t W = rec.n_words;
+    const uint32_t per = (W + T - 1) / T;
+    const uint32_t w0 = t * per < W ? t * per : W, w1 = w0 + per < W ? w0 + per : W;
+    uint32_t bits = 0;
+    {
+        uint32_t prev = w0 ? tk[w0 - 1] : 0u;
+        if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;  // prev is itself a distance word
+        for (uint32_t i = w0; i < w1; i++) {
+            const uint32_t w = tk[i];
+            uint32_t val, nb;
+            word_bits(s_codes, w, prev, val, nb);
+            bits += nb;
+            prev = (prev & 0x8000u) ? 0u : w;  // a distance word never introduces another one
+        }
+    }
+    uint32_t tok_bits;
+    const uint32_t my_off = bit0 + rec.hdr_bits + block_excl_scan(bits, s_tmp, &tok_bits);
+    const uint32_t eob = s_codes[EOB];
+    if (t == 0) {  // header bits, word by word
+        Emitter eh;
+        eh.begin(out32, bit0);
+        const uint32_t hb = rec.hdr_bits;
+        for (uint32_t i = 0; i < (hb >> 5); i++) eh.put(s_hdr[i], 32);
+        if (hb & 31) eh.put(s_hdr[hb >> 5] & ((1u << (hb & 31)) - 1), hb & 31);
+        eh.end();
+    }
+    Emitter em;
+    em.begin(out32, my_off);
+    {
+        uint32_t prev = w0 ? tk[w0 - 1] : 0u;
+        if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;
+        for (uint32_t i = w0; i < w1; i++) {
+            const uint32_t w = tk[i];
+            uint32_t val, nb;
+            word_bits(s_codes, w, prev, val, nb);
+            em.put(val, nb);
+            prev = (prev & 0x8000u) ? 0u : w;
+        }
+    }
+    em.end();
+    if (t == T - 1) {  // EOB follows all tokens
+        Emitter ee;
+        ee.begin(out32, bit0 + rec.hdr_bits + tok_bits);
+        ee.put(eob & 0xffffu, eob >> 16);
+        ee.end();
+    }
+    return bit0 + rec.hdr_bits + tok_bits + (eob >> 16);
+}
+
+__device__ __forceinline__ void put_be32(uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24);
+    p[1] = (uint8_t)(v >> 16);
+    p[2] = (uint8_t)(v >> 8);
+    p[3] = (uint8_t)v;
+}
+// zlib stream header (2 bytes, + DICTID when a preset dictionary is in use) at slot + 2
+__device__ __forceinline__ void put_zlib_header(const DeflArgs& a, uint8_t* slot) {
+    uint8_t cmf, flg;
+    zlib_header(a.dict_len != 0, cmf, flg);
+    slot[2] = cmf;
+    slot[3] = flg;
+    if (a.dict_len) put_be32(slot + 4, a.dict_adler);
+}
+
 __global__ void __launch_bounds__(T_ENCODE) encode_kernel(DeflArgs a) {
     __shared__ uint32_t s_codes[REC_WORDS];
     __shared__ uint32_t s_tmp[40];
@@ -875,74 +986,14 @@ __global__ void __launch_bounds__(T_ENCODE) encode_kernel(DeflArgs a) {
         const uint32_t n = rec.n;
         uint32_t stream_len;
         if (rec.mode != 0) {
-            for (uint32_t i = t; i < REC_WORDS; i += T) s_codes[i] = a.hist[(size_t)bj * REC_WORDS + i];
-            const uint32_t hbytes = (rec.hdr_bits + 7) >> 3;
-            for (uint32_t i = t; i < 160; i += T) s_hdr[i] = 0;
-            __syncthreads();
-            {
-                const uint8_t* gh = a.hdrs + (size_t)bj * 640;
-                uint8_t* sh = reinterpret_cast<uint8_t*>(s_hdr);
-                for (uint32_t i = t; i < hbytes; i += T) sh[i] = gh[i];
-            }
-            const uint16_t* tk = a.tokens + (size_t)bj * a.nmax;
-            const uint32_t W = rec.n_words;
-            const uint32_t per = (W + T - 1) / T;
-            const uint32_t w0 = t * per < W ? t * per : W, w1 = w0 + per < W ? w0 + per : W;
-            uint32_t bits = 0;
-            {
-                uint32_t prev = w0 ? tk[w0 - 1] : 0u;
-                if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;  // prev is itself a distance word
-                for (uint32_t i = w0; i < w1; i++) {
-                    const uint32_t w = tk[i];
-                    uint32_t val, nb;
-                    word_bits(s_codes, w, prev, val, nb);
-                    bits += nb;
-                    prev = (prev & 0x8000u) ? 0u : w;  // a distance word never introduces another one
-                }
-            }
-            uint32_t tok_bits;
-            const uint32_t my_off = rec.hdr_bits + block_excl_scan(bits, s_tmp, &tok_bits);
-            const uint32_t eob = s_codes[EOB];
-            const uint32_t total_bits = rec.hdr_bits + tok_bits + (eob >> 16);
-            const uint32_t body = (total_bits + 7) >> 3;
+            const uint32_t body = (rec.bits + 7) >> 3;
             stream_len = hdr_len + body + 4;
             // zero the deflate words (+ trailer spill) so shared boundary words can be OR-ed
             const uint32_t zw = (body + 4 + 3) >> 2;
             for (uint32_t i = t; i < zw; i += T) out32[i] = 0;
+            emit_block(a, bj, rec, out32, 0, s_codes, s_tmp, s_hdr);
             __syncthreads();
-            if (t == 0) {  // header bits: whole words stored, last partial word OR-ed
-                const uint32_t hb = rec.hdr_bits;
-                for (uint32_t i = 0; i < (hb >> 5); i++) out32[i] = s_hdr[i];
-                if (hb & 31) atomicOr(out32 + (hb >> 5), s_hdr[hb >> 5]);
-            }
-            Emitter em;
-            em.begin(out32, my_off);
-            {
-                uint32_t prev = w0 ? tk[w0 - 1] : 0u;
-                if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;
-                for (uint32_t i = w0; i < w1; i++) {
-                    const uint32_t w = tk[i];
-                    uint32_t val, nb;
-                    word_bits(s_codes, w, prev, val, nb);
-                    em.put(val, nb);
-                    prev = (prev & 0x8000u) ? 0u : w;
-                }
-            }
-            em.end();
-            if (t == T - 1) {  // EOB follows all tokens
-                Emitter ee;
-                ee.begin(out32, rec.hdr_bits + tok_bits);
-                ee.put(eob & 0xffffu, eob >> 16);
-                ee.end();
-            }
-            __syncthreads();
-            if (t == 0) {
-                uint8_t* tr = slot + 2 + hdr_len + body;
-                tr[0] = (uint8_t)(rec.adler >> 24);
-                tr[1] = (uint8_t)(rec.adler >> 16);
-                tr[2] = (uint8_t)(rec.adler >> 8);
-                tr[3] = (uint8_t)rec.adler;
-            }
+            if (t == 0) put_be32(slot + 2 + hdr_len + body, rec.adler);
         } else {
             // ---- stored block: n <= 32768 -> a single block ---------------------------------------
             const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
@@ -954,27 +1005,66 @@ __global__ void __launch_bounds__(T_ENCODE) encode_kernel(DeflArgs a) {
                 o[2] = (uint8_t)(n >> 8);
                 o[3] = (uint8_t)~n;
                 o[4] = (uint8_t)(~n >> 8);
-                uint8_t* tr = o + 5 + n;
-                tr[0] = (uint8_t)(rec.adler >> 24);
-                tr[1] = (uint8_t)(rec.adler >> 16);
-                tr[2] = (uint8_t)(rec.adler >> 8);
-                tr[3] = (uint8_t)rec.adler;
+                put_be32(o + 5 + n, rec.adler);
             }
             for (uint32_t p = t; p < n; p += T) o[5 + p] = src[p];
             stream_len = hdr_len + 5 + n + 4;
         }
         if (t == 0) {
-            uint8_t cmf, flg;
-            zlib_header(a.dict_len != 0, cmf, flg);
-            slot[2] = cmf;
-            slot[3] = flg;
-            if (a.dict_len) {
-                slot[4] = (uint8_t)(a.dict_adler >> 24);
-                slot[5] = (uint8_t)(a.dict_adler >> 16);
-                slot[6] = (uint8_t)(a.dict_adler >> 8);
-                slot[7] = (uint8_t)a.dict_adler;
-            }
+            put_zlib_header(a, slot);
             a.sizes[k] = stream_len;
+        }
+    }
+}
+
+// Long chunks: one CTA per chunk strings the coded blocks of its jobs together bit by bit.  If that is
+// not smaller than stored blocks the chunk is flagged for stored_kernel instead.
+struct LongArgs {
+    const uint32_t* chunk_k;      // selection slot of long chunk i
+    const uint32_t* chunk_first;  // its first job (index into the long job list)
+    const uint32_t* chunk_nblk;
+    uint8_t* stored_flag;         // [n_long]
+    uint32_t c0, c1;              // chunks of this batch
+};
+__global__ void __launch_bounds__(T_ENCODE) encode_long_kernel(DeflArgs a, LongArgs la) {
+    __shared__ uint32_t s_codes[REC_WORDS];
+    __shared__ uint32_t s_tmp[40];
+    __shared__ uint32_t s_hdr[160];
+    const uint32_t T = T_ENCODE, t = threadIdx.x;
+    for (uint32_t ci = la.c0 + blockIdx.x; ci < la.c1; ci += gridDim.x) {
+        __syncthreads();
+        const uint32_t k = la.chunk_k[ci], nblk = la.chunk_nblk[ci];
+        const uint32_t bj0 = la.chunk_first[ci] - a.job0;
+        const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
+        const uint64_t n = a.cuts[j] - (j ? a.cuts[j - 1] : a.start0);
+        uint64_t bits = 0;
+        for (uint32_t b = 0; b < nblk; b++) bits += a.recs[bj0 + b].bits;
+        const uint64_t body = (bits + 7) >> 3;
+        if (body >= n + 5 * (n / 65535 + 1)) {
+            if (t == 0) la.stored_flag[ci] = 1;
+            continue;
+        }
+        uint8_t* slot = a.stage + a.slot_off[k];
+        const uint32_t hdr_len = a.dict_len ? 6 : 2;
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(slot + 2 + hdr_len);
+        const uint64_t zw = (body + 4 + 3) >> 2;
+        for (uint64_t i = t; i < zw; i += T) out32[i] = 0;
+        uint32_t bit = 0, ad_a = 1, ad_b = 0;
+        for (uint32_t b = 0; b < nblk; b++) {
+            const ChunkRec rec = a.recs[bj0 + b];
+            bit = emit_block(a, bj0 + b, rec, out32, bit, s_codes, s_tmp, s_hdr);
+            // Adler-32 of a concatenation (zlib's adler32_combine)
+            const uint32_t a2 = rec.adler & 0xffffu, b2 = rec.adler >> 16;
+            const uint32_t rem = rec.n % 65521u;
+            ad_b = (uint32_t)((ad_b + b2 + (uint64_t)rem * ((ad_a + 65520u) % 65521u)) % 65521u);
+            ad_a = (ad_a + a2 + 65520u) % 65521u;
+        }
+        __syncthreads();
+        if (t == 0) {
+            put_be32(slot + 2 + hdr_len + body, (ad_b << 16) | ad_a);
+            put_zlib_header(a, slot);
+            a.sizes[k] = hdr_len + body + 4;
+            la.stored_flag[ci] = 0;
         }
     }
 }
@@ -1003,6 +1093,7 @@ __global__ void __launch_bounds__(256)
 stored_kernel(DeflArgs a) {
     __shared__ uint32_t s_a[256], s_b[256];
     for (uint32_t job = a.job0 + blockIdx.x; job < a.job1; job += gridDim.x) {
+        if (a.stored_flag && !a.stored_flag[job]) continue;   // block-uniform
         const uint32_t k = a.list[job];
         const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
         const uint64_t cs = j ? a.cuts[j - 1] : a.start0;
@@ -1056,6 +1147,60 @@ stored_kernel(DeflArgs a) {
                 slot[7] = (uint8_t)a.dict_adler;
             }
             a.sizes[k] = hdr_len + n + 5 * nblk + 4;
+        }
+        __syncthreads();
+    }
+}
+
+// job_k[i] holds an index into the class-2 list: replace it by the selection slot stored there
+__global__ void long_job_slot_kernel(uint32_t* __restrict__ job_k, uint32_t n, const uint32_t* __restrict__ list) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) job_k[i] = list[job_k[i]];
+}
+
+// lengths of the long chunks (class 2 list) for the host-side block plan
+__global__ void long_len_kernel(uint64_t start0, const uint64_t* __restrict__ cuts, const uint64_t* __restrict__ select,
+                                const uint32_t* __restrict__ list, uint32_t n, uint64_t* __restrict__ lens) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t j = select ? select[list[i]] : (uint64_t)list[i];
+    lens[i] = cuts[j] - (j ? cuts[j - 1] : start0);
+}
+
+// Index of the previous block for every batch job with block number >= 1: the same 16-byte bucket records the
+// host builds for the preset dictionary.  The four largest positions of a bucket are found by four rounds
+// of atomicMax (round r admits positions below the winner of round r-1), then each winner is dressed with
+// its tag and preceding byte.  One CTA per job; the records are read back through L2 (__ldcg).
+__global__ void __launch_bounds__(1024) long_dict_kernel(DeflArgs a) {
+    const uint32_t t = threadIdx.x;
+    const uint32_t n_jobs = a.job1 - a.job0;
+    for (uint32_t bj = blockIdx.x; bj < n_jobs; bj += gridDim.x) {
+        const uint32_t blkno = a.blk[a.job0 + bj];
+        if (!blkno) continue;
+        const uint32_t k = a.list[a.job0 + bj];
+        const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
+        const uint8_t* src = a.data + (j ? a.cuts[j - 1] : a.start0) + (uint64_t)(blkno - 1) * LONG_BLOCK;
+        DictDev* dd = const_cast<DictDev*>(a.long_dicts) + bj;
+        uint32_t* w = reinterpret_cast<uint32_t*>(dd->bk4);
+        for (uint32_t i = t; i < LONG_BLOCK + 32; i += 1024) dd->bytes[i] = i < LONG_BLOCK ? src[i] : (uint8_t)0;
+        for (uint32_t i = t; i < DICT_BUCKETS * 4; i += 1024) w[i] = 0;
+        __syncthreads();
+        auto le32 = [&](uint32_t q) {
+            return (uint32_t)src[q] | ((uint32_t)src[q + 1] << 8) | ((uint32_t)src[q + 2] << 16) | ((uint32_t)src[q + 3] << 24);
+        };
+        for (int r = 0; r < DICT_CAP; r++) {
+            for (uint32_t q = t; q + 3 < LONG_BLOCK; q += 1024) {
+                const uint32_t h = hash_dict(le32(q));
+                if (r == 0 || q + 1 < __ldcg(&w[h * 4 + r - 1])) atomicMax(&w[h * 4 + r], q + 1);
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = t; i < DICT_BUCKETS * 4; i += 1024) {
+            const uint32_t q1 = __ldcg(&w[i]);
+            if (q1) {
+                const uint32_t q = q1 - 1;
+                w[i] = 0x80000000u | dict_tag23(le32(q)) | ((q ? (uint32_t)src[q - 1] : DICT_PREV0) << 15) | q;
+            }
         }
         __syncthreads();
     }
@@ -1230,7 +1375,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         if (rc) return rc;
     }
     // misc: [slot_size m][slot_off m][sizes m+1][lists 3m u32][list_n 4 u32][totals][counters]
-    const size_t n_counters = 2 * (m / (BATCH_LARGE < BATCH_SMALL ? BATCH_LARGE : BATCH_SMALL) + 2);
+    const size_t n_counters = m + 8;   // one work counter per batch; a long chunk may be a batch of its own
     const size_t misc_bytes = (3 * m + 2) * 8 + 3 * m * 4 + 64 + n_counters * 4 + 64;
     HMSE_SCRATCH(ctx, misc, uint8_t*, SLOT_DEFLATE_MISC, misc_bytes);
     uint64_t* slot_size = (uint64_t*)misc;
@@ -1277,6 +1422,74 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     const uint32_t nmax_c[2] = {NMAX_SMALL, NMAX_LARGE};
     const uint32_t batch_c[2] = {BATCH_SMALL, BATCH_LARGE};
     const uint32_t ctas_c[2] = {(uint32_t)ctx->sm_count * 2, (uint32_t)ctx->sm_count};
+
+    // ---- plan of the long chunks (> NMAX_LARGE bytes): blocks of LONG_BLOCK bytes, batches aligned to chunks ----
+    const uint32_t n_long = n_class[2];
+    std::vector<uint32_t> job_k, job_blk, ch_first, ch_nblk, batch_c0, batch_j0;   // batches: chunk / job boundaries
+    std::vector<uint8_t> ch_stored;
+    uint32_t long_jobs_max = 0, n_long_coded = 0;
+    uint8_t* ldev = nullptr;   // [lens u64 n][first u32 n][nblk u32 n][flag u8 n (padded)][job_k][job_blk]
+    size_t off_first = 0, off_nblk = 0, off_flag = 0, off_jk = 0, off_jb = 0;
+    if (n_long) {
+        std::vector<uint64_t> lens(n_long);
+        HMSE_SCRATCH(ctx, lens_dev, uint64_t*, SLOT_DEFLATE_LONG, (size_t)n_long * 8);
+        KL(ctx);
+        long_len_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(start0, d_cuts, d_select, lists + 2 * m, n_long, lens_dev);
+        HMSE_LAUNCH_CHECK(ctx);
+        HMSE_CUDA(ctx, cudaMemcpyAsync(lens.data(), lens_dev, (size_t)n_long * 8, cudaMemcpyDeviceToHost, st));
+        HMSE_CUDA(ctx, cudaStreamSynchronize(st));
+        ch_first.resize(n_long);
+        ch_nblk.resize(n_long);
+        ch_stored.assign(n_long, 0);
+        batch_c0.push_back(0);
+        batch_j0.push_back(0);
+        for (uint32_t i = 0; i < n_long; i++) {
+            const uint64_t nb = (lens[i] + LONG_BLOCK - 1) / LONG_BLOCK;
+            ch_first[i] = (uint32_t)job_k.size();
+            if (level == 0 || nb > 2048) {   // level 0, or a chunk beyond 64 MiB: stored blocks
+                ch_nblk[i] = 0;
+                ch_stored[i] = 1;
+                continue;
+            }
+            ch_nblk[i] = (uint32_t)nb;
+            n_long_coded++;
+            if (job_k.size() - batch_j0.back() + nb > BATCH_LONG && job_k.size() > batch_j0.back()) {
+                batch_c0.push_back(i);
+                batch_j0.push_back((uint32_t)job_k.size());
+            }
+            for (uint32_t b = 0; b < nb; b++) {
+                job_k.push_back(0);   // filled on the device side from the list: the host does not know k
+                job_blk.push_back(b);
+            }
+        }
+        batch_c0.push_back(n_long);
+        batch_j0.push_back((uint32_t)job_k.size());
+        for (size_t b = 0; b + 1 < batch_j0.size(); b++)
+            if (batch_j0[b + 1] - batch_j0[b] > long_jobs_max) long_jobs_max = batch_j0[b + 1] - batch_j0[b];
+        const size_t nj = job_k.size();
+        off_first = (size_t)n_long * 8;
+        off_nblk = off_first + (size_t)n_long * 4;
+        off_flag = off_nblk + (size_t)n_long * 4;
+        off_jk = (off_flag + n_long + 15) & ~(size_t)15;
+        off_jb = off_jk + nj * 4;
+        HMSE_SCRATCH(ctx, ld2, uint8_t*, SLOT_DEFLATE_LONG, off_jb + nj * 4 + 16);
+        ldev = ld2;
+        HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_first, ch_first.data(), (size_t)n_long * 4, cudaMemcpyHostToDevice, st));
+        HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_nblk, ch_nblk.data(), (size_t)n_long * 4, cudaMemcpyHostToDevice, st));
+        HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_flag, ch_stored.data(), n_long, cudaMemcpyHostToDevice, st));
+        if (nj) {
+            // job -> selection slot: expand the chunk list by the block counts
+            for (uint32_t i = 0; i < n_long; i++)
+                for (uint32_t b = 0; b < ch_nblk[i]; b++) job_k[ch_first[i] + b] = i;   // index into the class list for now
+            HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_jk, job_k.data(), nj * 4, cudaMemcpyHostToDevice, st));
+            HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_jb, job_blk.data(), nj * 4, cudaMemcpyHostToDevice, st));
+            KL(ctx);
+            long_job_slot_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>((uint32_t*)(ldev + off_jk), (uint32_t)nj, lists + 2 * m);
+            HMSE_LAUNCH_CHECK(ctx);
+        }
+        HMSE_CUDA(ctx, cudaStreamSynchronize(st));   // the host vectors are pageable
+    }
+
     // work scratch: tokens (u16 per input byte, per batch job), hist/codes, headers, records, large-class match
     size_t tok_bytes = 0, rec_jobs = 1;
     for (int c = 0; c < 2; c++) {
@@ -1284,8 +1497,14 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         if ((size_t)jobs * nmax_c[c] * 2 > tok_bytes) tok_bytes = (size_t)jobs * nmax_c[c] * 2;
         if (jobs > rec_jobs) rec_jobs = jobs;
     }
+    if ((size_t)long_jobs_max * NMAX_LARGE * 2 > tok_bytes) tok_bytes = (size_t)long_jobs_max * NMAX_LARGE * 2;
+    if (long_jobs_max > rec_jobs) rec_jobs = long_jobs_max;
     tok_bytes = (tok_bytes + 255) & ~(size_t)255;
-    const uint32_t g_large = n_class[1] < ctas_c[1] ? n_class[1] : ctas_c[1];
+    uint32_t g_large = n_class[1] < ctas_c[1] ? n_class[1] : ctas_c[1];
+    if (long_jobs_max) {
+        const uint32_t g = long_jobs_max < ctas_c[1] ? long_jobs_max : ctas_c[1];
+        if (g > g_large) g_large = g;
+    }
     const size_t work_bytes = tok_bytes + rec_jobs * (REC_WORDS * 4 + 640 + sizeof(ChunkRec)) +
                               (size_t)g_large * (NMAX_LARGE + NMAX_LARGE / 32) * 4 + 1024;
     HMSE_SCRATCH(ctx, work, uint8_t*, SLOT_DEFLATE_WORK, work_bytes);
@@ -1294,9 +1513,15 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     a.hdrs = (uint8_t*)(a.hist + rec_jobs * REC_WORDS);
     a.recs = (ChunkRec*)(a.hdrs + rec_jobs * 640);
     a.match = (uint32_t*)(a.recs + rec_jobs);
+    DictDev* long_dicts = nullptr;
+    if (long_jobs_max) {
+        HMSE_SCRATCH(ctx, ldicts, DictDev*, SLOT_DEFLATE_LDICT, (size_t)long_jobs_max * sizeof(DictDev));
+        long_dicts = ldicts;
+    }
 
     HT_BEGIN(ctx, HT_DEFLATE, st);
     uint32_t ci = 0;
+    const uint32_t hmax = (uint32_t)ctx->sm_count * 3, emax = (uint32_t)ctx->sm_count * 8;
     for (int c = 0; c < 2; c++) {
         a.list = lists + (size_t)c * m;
         a.nmax = nmax_c[c];
@@ -1310,23 +1535,57 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             parse_kernel<<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
             if (level != 0) {
                 const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
-                const uint32_t hmax = (uint32_t)ctx->sm_count * 3;
                 KL(ctx);
                 huffman_kernel<<<hb < hmax ? hb : hmax, HUFF_WARPS * 32, sm_huff, st>>>(a);
             }
-            const uint32_t emax = (uint32_t)ctx->sm_count * 8;
             KL(ctx);
             encode_kernel<<<jobs < emax ? jobs : emax, T_ENCODE, 0, st>>>(a);
             HMSE_LAUNCH_CHECK(ctx);
         }
     }
-    if (n_class[2]) {
+    if (n_long) {
+        // coded long chunks, batch by batch: previous-block indexes, parse, Huffman, bit-level concatenation
+        LongArgs la;
+        la.chunk_k = lists + 2 * m;
+        la.chunk_first = (const uint32_t*)(ldev + off_first);
+        la.chunk_nblk = (const uint32_t*)(ldev + off_nblk);
+        la.stored_flag = ldev + off_flag;
+        a.nmax = NMAX_LARGE;
+        a.match_smem = 0;
+        a.list = (const uint32_t*)(ldev + off_jk);
+        a.blk = (const uint32_t*)(ldev + off_jb);
+        a.long_dicts = long_dicts;
+        for (size_t b = 0; n_long_coded && b + 1 < batch_j0.size(); b++) {
+            a.job0 = batch_j0[b];
+            a.job1 = batch_j0[b + 1];
+            const uint32_t jobs = a.job1 - a.job0;
+            if (!jobs) continue;
+            a.counter = counters + ci++;
+            KL(ctx);
+            long_dict_kernel<<<jobs < (uint32_t)ctx->sm_count ? jobs : (uint32_t)ctx->sm_count, 1024, 0, st>>>(a);
+            KL(ctx);
+            parse_kernel<<<jobs < ctas_c[1] ? jobs : ctas_c[1], T_PARSE, sm_parse[1], st>>>(a);
+            const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
+            KL(ctx);
+            huffman_kernel<<<hb < hmax ? hb : hmax, HUFF_WARPS * 32, sm_huff, st>>>(a);
+            la.c0 = batch_c0[b];
+            la.c1 = batch_c0[b + 1];
+            const uint32_t nc = la.c1 - la.c0;
+            KL(ctx);
+            encode_long_kernel<<<nc < emax ? nc : emax, T_ENCODE, 0, st>>>(a, la);
+            HMSE_LAUNCH_CHECK(ctx);
+        }
+        // whatever stays (level 0, oversize, or not compressible): stored blocks
         a.list = lists + 2 * m;
+        a.blk = nullptr;
+        a.long_dicts = nullptr;
+        a.stored_flag = ldev + off_flag;
         a.job0 = 0;
-        a.job1 = n_class[2];
+        a.job1 = n_long;
         KL(ctx);
-        stored_kernel<<<n_class[2] < 1024 ? n_class[2] : 1024, 256, 0, st>>>(a);
+        stored_kernel<<<n_long < 1024 ? n_long : 1024, 256, 0, st>>>(a);
         HMSE_LAUNCH_CHECK(ctx);
+        a.stored_flag = nullptr;
     }
     HT_END(ctx, HT_DEFLATE, st);
     HMSE_CUDA(ctx, cudaMemsetAsync(sizes + m, 0, 8, st));

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 class Params(C.Structure):
     _fields_ = [("hash_bytes", C.c_int), ("chain_own", C.c_int), ("chain_dict", C.c_int), ("lazy", C.c_int),
-                ("too_far", C.c_int), ("dict_hash_bits", C.c_int), ("mode", C.c_int), ("min_len", C.c_int)]
+                ("too_far", C.c_int), ("dict_hash_bits", C.c_int), ("mode", C.c_int), ("min_len", C.c_int), ("hist", C.c_int)]
 
 
 def build(force=False):

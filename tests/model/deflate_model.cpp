@@ -21,6 +21,7 @@ struct Params {
     int mode;         // 0: every position extends its candidates; 1: run heads only + prefix max (skip a pair
                       // only when the previous position examined its predecessor); 2: same, unconditional skip
     int min_len;      // shortest match emitted (0 -> hash_bytes)
+    int hist;         // the first `hist` bytes are history only: searched, not emitted (multi-block chunks)
 };
 
 static inline uint32_t rd(const uint8_t* p, int nb) {
@@ -165,7 +166,7 @@ extern "C" int64_t model_compress(const uint8_t* data, uint32_t n, const uint8_t
     // parse
     std::vector<uint32_t> tok;  // literal: byte ; match: 1<<31 | len<<16 | (dist-1)
     uint32_t lit_freq[288] = {0}, dist_freq[32] = {0};
-    uint32_t p = 0, n_match = 0;
+    uint32_t p = (uint32_t)pr->hist, n_match = 0;
     while (p < n) {
         uint32_t L = mlen[p];
         bool lit = L < 3;

@@ -78,13 +78,45 @@ def test_fixed_size_chunks(ctx, corpus8, kib):
     assert r >= 0.98
 
 
-def test_64k_chunks_roundtrip(ctx, corpus8):
+def test_64k_chunks_ratio_and_roundtrip(ctx, corpus8):
+    # BASELINE.json config 3, 64 KiB row: chunks longer than 32 KiB become multi-block streams whose blocks
+    # see the previous 32 KiB (zlib's window), so the ratio bar holds there too
     import hmse_b200
-    d = corpus8[:2 << 20]
+    d = corpus8[:4 << 20]
     cuts = np.arange(65536, d.size + 1, 65536, dtype=np.uint64)
     zd = corpus.zdict()
     blob, offs = hmse_b200.compress(d, cuts, None, zd, ctx=ctx)
     _roundtrip(d, cuts, None, zd, blob, offs)
+    r = _ratio_vs_zlib(d, cuts, None, zd, blob)
+    print("64 KiB: zlib6/gpu bytes = %.4f" % r)
+    assert r >= 0.98
+
+
+def test_long_chunks_mixed(ctx, corpus8):
+    # ragged long chunks (block edges at 32 KiB multiples +-1, a 1 MiB chunk, > 96 blocks in one call so that
+    # several batches run), mixed with short ones, with and without a dictionary, level 0, incompressible
+    import hmse_b200
+    rng = np.random.default_rng(3)
+    lens = [32769, 65535, 65536, 65537, 98304, 100, 40000, 1 << 20, 8192, 3 * 32768 + 5, 200000] + [70000] * 60
+    d = corpus8[:sum(lens)].copy()
+    d[300000:300000 + 150000] = rng.integers(0, 256, 150000, dtype=np.uint8)   # incompressible stretch
+    cuts = np.cumsum(lens).astype(np.uint64)
+    zd = corpus.zdict()
+    for z in (zd, b""):
+        blob, offs = hmse_b200.compress(d, cuts, None, z, ctx=ctx)
+        _roundtrip(d, cuts, None, z, blob, offs)
+        assert _ratio_vs_zlib(d, cuts, None, z, blob) >= 0.975
+        blob2, offs2 = hmse_b200.compress(d, cuts, None, z, ctx=ctx)
+        assert np.array_equal(blob, blob2) and np.array_equal(offs, offs2)      # deterministic
+    blob0, offs0 = hmse_b200.compress(d, cuts, None, zd, level=0, ctx=ctx)
+    _roundtrip(d, cuts, None, zd, blob0, offs0)
+    sizes = np.diff(offs.astype(np.int64))
+    assert (sizes <= np.array([hmse_b200.compress_bound(int(n)) for n in lens])).all()
+    r = rng.integers(0, 256, 200000, dtype=np.uint8)
+    rc = np.array([70000, 200000], dtype=np.uint64)
+    blob, offs = hmse_b200.compress(r, rc, None, zd, ctx=ctx)
+    _roundtrip(r, rc, None, zd, blob, offs)
+    assert blob.size <= r.size + 64
 
 
 def test_header_bytes_and_dictid(ctx, corpus8):
