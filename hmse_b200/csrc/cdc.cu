@@ -2,10 +2,10 @@
 // against the sequential algorithm (spec: README.md:289, 1202-1256, 2434-2514; algorithm per the
 // paper the spec cites at README.md:2753-2755; restated in oracle/cdc.py).
 //
-// K1 gear_scan     reads the stream ONCE.  Tiles of 64 KiB are staged into shared memory with
-//                  per-thread 256-byte bulk-async (TMA) copies into bank-conflict-free padded
+// K1 gear_scan     reads the stream ONCE.  Tiles of 32 KiB are staged into shared memory with
+//                  per-thread 128-byte bulk-async (TMA) copies into bank-conflict-free padded
 //                  slots, double buffered on mbarriers.  A 64-bit Gear hash depends only on
-//                  the trailing 64 bytes, so every thread rolls its own 256-byte run after a
+//                  the trailing 64 bytes, so every thread rolls its own 128-byte run after a
 //                  64-byte warm-up and emits one MaskS bit and one MaskL bit per byte.
 // K2 resolve       sequential FastCDC resets fp at start+min, so next_cut(s) is a pure
 //                  function of s: partial-window positions (64 bytes after the skip) are
@@ -29,8 +29,9 @@ struct CdcDev {
 // K1: gear scan
 // ------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 256;
-constexpr int K1_RUN = 256;                     // bytes rolled per thread per tile
-constexpr int K1_TILE = K1_THREADS * K1_RUN;    // 64 KiB
+constexpr int K1_RUN = 128;                     // bytes rolled per thread per tile (+64 of warm-up)
+constexpr int K1_CTAS = 3;                      // resident CTAs per SM: the staging buffers, not the registers, bound it
+constexpr int K1_TILE = K1_THREADS * K1_RUN;    // 32 KiB
 constexpr int K1_SLOT = K1_RUN + 16;            // padded slot stride: LDS.128 conflict-free
 constexpr int K1_STAGE = (K1_THREADS + 1) * K1_SLOT;  // slot 0 carries the 64-byte halo
 constexpr int K1_STAGES = 2;
@@ -87,7 +88,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     fp = (fp << 1) + sg[((W) >> 16) & 0xffu];     \
     fp = (fp << 1) + sg[(W) >> 24];
 
-__global__ void __launch_bounds__(K1_THREADS, 1)
+__global__ void __launch_bounds__(K1_THREADS, K1_CTAS)
 gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles, const CdcDev* __restrict__ cfg,
                  uint64_t* __restrict__ bitS, uint64_t* __restrict__ bitL) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -131,7 +132,8 @@ gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles,
 
         const uint8_t* st = stage0 + (size_t)s * K1_STAGE;
         const uint64_t pos = tile * (uint64_t)K1_TILE + (uint64_t)t * K1_RUN;
-        uint64_t sw[4] = {0, 0, 0, 0}, lw[4] = {0, 0, 0, 0};
+        uint64_t sw[K1_RUN / 64] = {0, 0}, lw[K1_RUN / 64] = {0, 0};
+        static_assert(K1_RUN == 128, "two 64-bit words per mask per thread");
         if (pos < n) {
             uint64_t fp = 0;
             if (pos >= 64) {
@@ -145,7 +147,7 @@ gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles,
             }
             const uint4* rp = reinterpret_cast<const uint4*>(st + (size_t)(t + 1) * K1_SLOT);
 #pragma unroll
-            for (int w = 0; w < 4; w++) {
+            for (int w = 0; w < K1_RUN / 64; w++) {
                 uint64_t sb = 0, lb = 0;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -162,21 +164,19 @@ gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles,
             const uint64_t left = n - pos;
             if (left < K1_RUN) {
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
+                for (int w = 0; w < K1_RUN / 64; w++) {
                     uint64_t keep = left >= 64ull * (w + 1) ? ~0ull : (left <= 64ull * w ? 0ull : ((1ull << (left - 64 * w)) - 1));
                     sw[w] &= keep;
                     lw[w] &= keep;
                 }
             }
         }
-        // 4 words per mask per thread: lanes are contiguous -> 1 KiB coalesced per warp
+        // 2 words per mask per thread: lanes are contiguous -> 512 B coalesced per warp
         const uint64_t wbase = pos >> 6;
         uint4* os = reinterpret_cast<uint4*>(bitS + wbase);
         uint4* ol = reinterpret_cast<uint4*>(bitL + wbase);
         os[0] = make_uint4((uint32_t)sw[0], (uint32_t)(sw[0] >> 32), (uint32_t)sw[1], (uint32_t)(sw[1] >> 32));
-        os[1] = make_uint4((uint32_t)sw[2], (uint32_t)(sw[2] >> 32), (uint32_t)sw[3], (uint32_t)(sw[3] >> 32));
         ol[0] = make_uint4((uint32_t)lw[0], (uint32_t)(lw[0] >> 32), (uint32_t)lw[1], (uint32_t)(lw[1] >> 32));
-        ol[1] = make_uint4((uint32_t)lw[2], (uint32_t)(lw[2] >> 32), (uint32_t)lw[3], (uint32_t)(lw[3] >> 32));
         __syncthreads();  // everyone is done reading stage s before it is refilled
     }
 }
@@ -438,7 +438,8 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
     if (n_tiles) {
         HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)K1_SMEM));
-        uint64_t grid = n_tiles < (uint64_t)ctx->sm_count ? n_tiles : (uint64_t)ctx->sm_count;
+        const uint64_t resident = (uint64_t)ctx->sm_count * K1_CTAS;
+        uint64_t grid = n_tiles < resident ? n_tiles : resident;
         HT_BEGIN(ctx, HT_SCAN, st);
         KL(ctx);
         gear_scan_kernel<<<(unsigned)grid, K1_THREADS, K1_SMEM, st>>>(

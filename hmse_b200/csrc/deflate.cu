@@ -51,6 +51,9 @@ constexpr uint32_t BATCH_SMALL = 32768, BATCH_LARGE = 8192;  // chunks per batch
 // dictionary (indexed on the device), which gives every position zlib's full 32 KiB window.
 constexpr uint32_t LONG_BLOCK = 32768;
 constexpr uint32_t BATCH_LONG = 96;   // blocks per batch: each carries a 0.5 MB dictionary index
+// log2 of the range length of the chain passes in the small class.  16-byte ranges keep all 512 threads busy on an
+// 8 KiB chunk but double the range-to-range hops of P6; measured slower (kt20 vs kt21), so both classes use 32.
+constexpr int RS_SMALL = 5;
 constexpr uint32_t REC_WORDS = 320;                          // 288 lit/len + 32 dist counters / codes
 
 // Device image of the dictionary index (SLOT_DEFLATE_DICT), built on the host once per dictionary.
@@ -233,7 +236,9 @@ __device__ __forceinline__ bool mw_is_match(uint32_t mw) { return (mw >> 16) != 
 // =================================================================================================
 // parse_kernel
 // =================================================================================================
+template <int RS>   // log2 of the range length of the chain passes P4c-P7
 __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
+    constexpr uint32_t RL = 1u << RS;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t T = blockDim.x, t = threadIdx.x;
     const unsigned lane = t & 31, warp = t >> 5, nwarps = T >> 5;
@@ -244,9 +249,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     uint16_t* s_sorted = reinterpret_cast<uint16_t*>(smem + nmax + 16);        // nmax u16 (later: exits, skewed)
     uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + nmax + 16 + 2 * (size_t)(nmax + nmax / 32));  // CNT_WORDS
     uint16_t* s_E = reinterpret_cast<uint16_t*>(s_cnt32);  // bucket h = sorted[E[h] .. E[h+1])
-    uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CNT_WORDS);         // nmax/32 bytes
-    uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_entry + nmax / 32);        // nmax bits
-    ParseSm* sm = reinterpret_cast<ParseSm*>(s_flag + nmax / 32);
+    uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CNT_WORDS);         // nmax/16 bytes: entry offset of every range
+    ParseSm* sm = reinterpret_cast<ParseSm*>(s_entry + nmax / 16);
     uint8_t* s_tail = reinterpret_cast<uint8_t*>(sm) + ((sizeof(ParseSm) + 15) & ~15u);
     // small class: match words in shared memory (skewed); the list of buckets to sort borrows that
     // space before P4.  large class: match words in global scratch, the list has its own space.
@@ -278,11 +282,14 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
         const DictDev* dict = blkno ? a.long_dicts + bj : a.dict;
         const uint32_t dlen = blkno ? LONG_BLOCK : a.dict_len;
 
-        // ---- P0: stage the chunk (byte-unaligned source -> aligned words), clear tables -----
+        // ---- P0: stage the chunk (byte-unaligned source -> aligned words) with its Adler-32 partial sums
+        //      taken from the words in flight (byte sum and position-weighted byte sum of a word are one
+        //      instruction each), clear tables ---------------------------------------------------------
         {
             const uint32_t kmis = (uint32_t)((uintptr_t)src & 3);
             const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(src - kmis);
             const uint32_t nw = (n + 3) >> 2;
+            uint32_t sa = 0, sb = 0;   // sb <= 16 words x 32768 x 1020 per thread: no overflow
             for (uint32_t i = t; i < nw + 4 && i < (nmax + 16) / 4; i += T) {
                 uint32_t v = 0;
                 if (i < nw) {
@@ -291,41 +298,45 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     v = __funnelshift_r(lo, hi, kmis * 8);
                     const uint32_t rem = n - 4 * i;  // bytes of this word inside the chunk
                     if (rem < 4) v &= (1u << (8 * rem)) - 1;
+                    const uint32_t bs = __vsadu4(v, 0u);
+                    sa += bs;
+                    sb += (n - 4 * i) * bs - __dp4a(v, 0x03020100u, 0u);   // sum over bytes of (n - position) * byte
                 }
                 s_data32[i] = v;
             }
             for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;
             for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
-        }
-        __syncthreads();
-        PROF(0)
-        const uint32_t nh = n >= 4 ? n - 3 : 0;  // hashed positions
-
-        // ---- Adler-32 of the chunk (parallel partial sums, n <= 32768) --------------------
-        {
-            uint32_t sa = 0, sb = 0;
-            for (uint32_t p = t; p < n; p += T) {
-                uint32_t b = s_data[p];
-                sa += b;
-                sb += (n - p) * b;  // <= 32768*255 per term, <= 64 terms per thread
-                if (sb >= 0x80000000u) sb %= 65521u;
-            }
             sb %= 65521u;
             uint32_t tot_a, tot_b;
-            block_excl_scan(sa, sm->warp_tmp, &tot_a);
+            block_excl_scan(sa, sm->warp_tmp, &tot_a);   // (these also order the staging before its readers)
             block_excl_scan(sb, sm->warp_tmp, &tot_b);
             if (t == 0) {
                 sm->adler_a = (1u + tot_a) % 65521u;
                 sm->adler_b = (n % 65521u + tot_b) % 65521u;
             }
         }
+        __syncthreads();
+        PROF(0)
+        const uint32_t nh = n >= 4 ? n - 3 : 0;  // hashed positions
         PROF(1)
         uint32_t n_words = 0;
+        // 13-bit hash of every position, kept for the scatter and the bucket fix-up (upper half of the match words,
+        // which are not written before P4)
+        uint16_t* s_h16 = reinterpret_cast<uint16_t*>(mptr) + nmax;
         if (a.level != 0) {
-            // ---- P1: hash histogram (count of bucket h lives at E[h+1]) ----------------------------
-            for (uint32_t p = t; p < nh; p += T) {
-                const uint32_t h1 = hash4(ld32u(s_data32, p)) + 1;
-                atomicAdd(&s_cnt32[h1 >> 1], 1u << (16 * (h1 & 1)));
+            // ---- P1: hash histogram (count of bucket h lives at E[h+1]); four positions per step from two words ----
+            for (uint32_t i = t; 4 * i < nh; i += T) {
+                const uint32_t w0 = s_data32[i], w1 = s_data32[i + 1];
+                uint32_t hh[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    hh[q] = hash4(q ? __funnelshift_r(w0, w1, 8 * q) : w0);
+                    if (4 * i + q < nh) {
+                        const uint32_t h1 = hh[q] + 1;
+                        atomicAdd(&s_cnt32[h1 >> 1], 1u << (16 * (h1 & 1)));
+                    }
+                }
+                reinterpret_cast<uint2*>(s_h16)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
             }
             __syncthreads();
             // ---- P2: exclusive scan: E[h+1] = start of bucket h (cursor), E[0] = 0 ------------------
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             for (uint32_t p0 = 0; p0 < nh; p0 += T) {
                 const uint32_t p = p0 + t;
                 if (p < nh) {
-                    const uint32_t h1 = hash4(ld32u(s_data32, p)) + 1;
+                    const uint32_t h1 = (uint32_t)s_h16[p] + 1;
                     const uint32_t sh = 16 * (h1 & 1);
                     const uint32_t old = atomicAdd(&s_cnt32[h1 >> 1], 1u << sh);
                     s_sorted[(old >> sh) & 0xffffu] = (uint16_t)p;
@@ -370,19 +381,19 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     const uint32_t tile = p >> TILE_SHIFT;
                     const uint32_t ql = i ? s_sorted[i - 1] : 0xffffffffu, qr = i + 1 < nh ? s_sorted[i + 1] : 0xffffffffu;
                     if ((ql >> TILE_SHIFT) != tile && (qr >> TILE_SHIFT) != tile) continue;
-                    const uint32_t h = hash4(ld32u(s_data32, p));
+                    const uint32_t h = s_h16[p];
                     uint32_t first = i, smaller = 0, others = 0;
                     for (uint32_t j = i; j > 0;) {   // left neighbours of the same tile and bucket
                         j--;
                         const uint32_t q = s_sorted[j];
-                        if ((q >> TILE_SHIFT) != tile || hash4(ld32u(s_data32, q)) != h) break;
+                        if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
                         first = j;
                         smaller += q < p;
                         others++;
                     }
                     for (uint32_t j = i + 1; j < nh; j++) {
                         const uint32_t q = s_sorted[j];
-                        if ((q >> TILE_SHIFT) != tile || hash4(ld32u(s_data32, q)) != h) break;
+                        if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
                         smaller += q < p;
                         others++;
                     }
@@ -509,8 +520,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             __syncthreads();
             PROF(5)
 
-            // ranges of 32 positions, blocked over threads
-            const uint32_t R = (n + 31) >> 5;
+            // ranges of RL positions (16 in the small class, so that all threads have one; 32 in the large),
+            // blocked over threads; within a range the skewed index is SK(first) + offset
+            const uint32_t R = (n + RL - 1) >> RS;
             const uint32_t rpt = (R + T - 1) / T;
             const uint32_t r0 = t * rpt, r1 = (r0 + rpt < R) ? r0 + rpt : R;
             // ---- P4c: run keys -> match words: a forward prefix max over positions (thread-local over its
@@ -518,21 +530,23 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             {
                 uint32_t loc = 0;
                 for (uint32_t r = r0; r < r1; r++) {
-                    const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
-                    for (uint32_t p = ps; p < pe; p++) loc = max(loc, mptr[SK(p)]);
+                    const uint32_t ps = r << RS, cnt = (ps + RL < n) ? RL : n - ps;
+                    const uint32_t* mp = mptr + SK(ps);
+                    for (uint32_t q = 0; q < cnt; q++) loc = max(loc, mp[q]);
                 }
                 uint32_t run = block_excl_scan_max(loc, sm->warp_tmp);
                 for (uint32_t r = r0; r < r1; r++) {
-                    const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
-                    for (uint32_t p = ps; p < pe; p++) {
-                        run = max(run, mptr[SK(p)]);
-                        const uint32_t end = run >> 15;
+                    const uint32_t ps = r << RS, cnt = (ps + RL < n) ? RL : n - ps;
+                    uint32_t* mp = mptr + SK(ps);
+                    for (uint32_t q = 0; q < cnt; q++) {
+                        run = max(run, mp[q]);
+                        const uint32_t end = run >> 15, p = ps + q;
                         uint32_t mw = 0;
                         if (end >= p + 4) {
                             const uint32_t L = min(end - p, (uint32_t)MAX_MATCH);
                             mw = (L << 16) | (32767u - (run & 0x7fffu));
                         }
-                        mptr[SK(p)] = mw;
+                        mp[q] = mw;
                     }
                 }
             }
@@ -540,15 +554,17 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             PROF(9)
             // ---- P5: backward DP: exit[p] = first chain position past p's range -------------
             for (uint32_t r = r0; r < r1; r++) {
-                const uint32_t ps = r << 5, pe = (ps + 32 < n) ? ps + 32 : n;
+                const uint32_t ps = r << RS, pe = (ps + RL < n) ? ps + RL : n;
                 uint32_t nxt_len = pe < n ? (mptr[SK(pe)] >> 16) : 0;
-                for (uint32_t p = pe; p-- > ps;) {
-                    const uint32_t mw = mptr[SK(p)];
+                uint32_t* mp = mptr + SK(ps);
+                uint16_t* xp = s_exit + SK(ps);
+                for (uint32_t q = pe - ps; q-- > 0;) {
+                    const uint32_t mw = mp[q];
                     const uint32_t L = mw >> 16;
                     const bool lazy_lit = L != 0 && L < (uint32_t)MAX_LAZY && nxt_len > L;
-                    if (lazy_lit) mptr[SK(p)] = mw | 0x8000u;
-                    const uint32_t next = (L == 0 || lazy_lit) ? p + 1 : p + L;
-                    s_exit[SK(p)] = (uint16_t)(next >= pe ? next : s_exit[SK(next)]);
+                    if (lazy_lit) mp[q] = mw | 0x8000u;
+                    const uint32_t next = ps + q + ((L == 0 || lazy_lit) ? 1u : L);
+                    xp[q] = (uint16_t)(next >= pe ? next : xp[next - ps]);
                     nxt_len = L;
                 }
             }
@@ -596,7 +612,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         const uint32_t be = ((blk << 10) + 1024 < n) ? (blk << 10) + 1024 : n;
                         uint32_t p = s_bentry[blk];
                         while (p < be) {
-                            s_entry[p >> 5] = (uint8_t)(p & 31);
+                            s_entry[p >> RS] = (uint8_t)(p & (RL - 1));
                             p = s_exit[SK(p)];
                         }
                     }
@@ -609,8 +625,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             for (uint32_t r = r0; r < r1; r++) {
                 const uint32_t e = s_entry[r];
                 if (e == 0xFF) continue;
-                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
-                for (uint32_t p = (r << 5) + e; p < pe;) {
+                const uint32_t pe = ((r << RS) + RL < n) ? (r << RS) + RL : n;
+                for (uint32_t p = (r << RS) + e; p < pe;) {
                     const uint32_t mw = mptr[SK(p)];
                     if (mw_is_match(mw)) {
                         uint32_t sy, eb, ev;
@@ -632,8 +648,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             for (uint32_t r = r0; r < r1; r++) {
                 const uint32_t e = s_entry[r];
                 if (e == 0xFF) continue;
-                const uint32_t pe = ((r << 5) + 32 < n) ? (r << 5) + 32 : n;
-                for (uint32_t p = (r << 5) + e; p < pe;) {
+                const uint32_t pe = ((r << RS) + RL < n) ? (r << RS) + RL : n;
+                for (uint32_t p = (r << RS) + e; p < pe;) {
                     const uint32_t mw = mptr[SK(p)];
                     if (mw_is_match(mw)) {
                         tk[w_off++] = (uint16_t)(0x8000u | (mw >> 16));
@@ -712,19 +728,68 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
             __syncwarp();
         }
         const uint32_t k_used = used;
-        // rank sort of the literal/length alphabet by (freq, symbol)
-        for (uint32_t sy = lane; sy < (uint32_t)NLIT; sy += 32) {
-            const uint32_t f = s.freq[sy];
-            s.dh.lit_lens[sy] = 0;
-            if (f) {
-                uint32_t rank = 0;
-                for (uint32_t o = 0; o < (uint32_t)NLIT; o++) {
-                    const uint32_t gq = s.freq[o];
-                    rank += (gq != 0) && (gq < f || (gq == f && o < sy));
+        // leaves of the literal/length tree sorted by (freq, symbol): a stable LSD radix sort of the used symbols,
+        // two passes of 8 bits (freq <= 32768); in-pass ranks from match_any groups taken in symbol order
+        for (uint32_t sy = lane; sy < (uint32_t)NLIT; sy += 32) s.dh.lit_lens[sy] = 0;
+        {
+            uint32_t* hist = s.hw.w + 288;   // 256 counters; the leaves (< 288) and the merge do not reach them yet
+            uint32_t* tf = s.codes;          // pass-1 output: frequencies ...
+            uint16_t* ts = s.hw.parent;      // ... and symbols (both are written for real only later)
+            const uint32_t lt = (1u << lane) - 1;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                const uint32_t count = pass ? k_used : (uint32_t)NLIT;
+                for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+                __syncwarp();
+                for (uint32_t i = lane; i < count; i += 32) {
+                    const uint32_t f = pass ? tf[i] : s.freq[i];
+                    if (f) atomicAdd(&hist[(f >> (8 * pass)) & 255u], 1u);
                 }
-                s.hw.w[rank] = f;
-                s.hw.order[rank] = (uint16_t)sy;
+                __syncwarp();
+                {   // exclusive scan: lane owns bins 8*lane .. 8*lane+7
+                    uint32_t c[8], sum = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        c[q] = hist[8 * lane + q];
+                        sum += c[q];
+                    }
+                    uint32_t inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (unsigned)o) inc += tt;
+                    }
+                    uint32_t run = inc - sum;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        hist[8 * lane + q] = run;
+                        run += c[q];
+                    }
+                }
+                __syncwarp();
+                for (uint32_t base = 0; base < count; base += 32) {
+                    const uint32_t i = base + lane;
+                    const uint32_t f = i < count ? (pass ? tf[i] : s.freq[i]) : 0u;
+                    const uint32_t sy = pass ? (uint32_t)ts[i < count ? i : 0] : i;
+                    const uint32_t d = (f >> (8 * pass)) & 255u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, f ? d : 256u + lane);
+                    const uint32_t rank = __popc(peers & lt);
+                    const uint32_t off = f ? hist[d] : 0u;
+                    __syncwarp();
+                    if (f) {
+                        if (pass) {
+                            s.hw.w[off + rank] = f;
+                            s.hw.order[off + rank] = (uint16_t)sy;
+                        } else {
+                            tf[off + rank] = f;
+                            ts[off + rank] = (uint16_t)sy;
+                        }
+                        if (rank == 0) hist[d] = off + __popc(peers);
+                    }
+                    __syncwarp();
+                }
             }
+            for (uint32_t i = lane; i < REC_WORDS; i += 32) s.codes[i] = 0;   // the sort borrowed them
         }
         __syncwarp();
         if (lane == 0) huff_merge(s.hw, (int)k_used);
@@ -765,35 +830,58 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
             s.dh.lit_lens[s.hw.order[i]] = (uint8_t)L;
         }
         __syncwarp();
-        if (lane == 0) plan_header_from_lengths(s.dh, s.hw);  // RLE + code-length code (serial, small)
-        // canonical codes + block cost (lanes 1..31; lane 0 is busy with the header plan)
-        if (lane) {
+        // canonical codes + block cost, both trees: per-length counts -> first code of every length (lane 0),
+        // then the symbols in order, 32 at a time: code = first[len] + symbols of that length seen so far
+        {
+            uint32_t* cnt = s.bl32;          // [16] per-length counts, then first codes
+            uint32_t* seen = s.hw2.w;        // [16] running counts (the distance-tree scratch is free again)
+            const uint32_t lt = (1u << lane) - 1;
             uint32_t cd = 0, cf = 0;
-            for (uint32_t q = lane - 1; q < (uint32_t)NLIT + NDIST; q += 31) {
-                const bool is_dist = q >= (uint32_t)NLIT;
-                const uint32_t sy = is_dist ? q - NLIT : q;
-                const uint8_t* lens = is_dist ? s.dh.dist_lens : s.dh.lit_lens;
-                const uint32_t nsy = is_dist ? NDIST : NLIT;
-                const uint32_t l = lens[sy];
-                uint32_t code = 0;
-                if (l) {
-                    uint32_t nc = 0, same_before = 0;
-                    for (uint32_t o = 0; o < nsy; o++) {
-                        const uint32_t lo_ = lens[o];
-                        if (lo_ && lo_ < l) nc += 1u << (l - lo_);  // next_code[l] = sum count[b] << (l-b), b < l
-                        same_before += (lo_ == l) && (o < sy);
-                    }
-                    code = (l << 16) | bitrev(nc + same_before, (int)l);
+#pragma unroll 1
+            for (int tree = 0; tree < 2; tree++) {
+                const uint8_t* lens = tree ? s.dh.dist_lens : s.dh.lit_lens;
+                const uint32_t nsy = tree ? NDIST : NLIT, cbase = tree ? 288u : 0u;
+                if (lane < 16) {
+                    cnt[lane] = 0;
+                    seen[lane] = 0;
                 }
-                const uint32_t f = g[is_dist ? 288 + sy : sy];  // true counts (without the forced code)
-                const uint32_t xb = is_dist ? (uint32_t)dsym_extra((int)sy) : (sy > 256 ? (uint32_t)lsym_extra((int)sy) : 0u);
-                cd += f * (l + xb);
-                cf += f * ((is_dist ? 5u : (uint32_t)fixed_lit_len((int)sy)) + xb);
-                s.codes[is_dist ? 288 + sy : sy] = code;
+                __syncwarp();
+                for (uint32_t sy = lane; sy < nsy; sy += 32)
+                    if (lens[sy]) atomicAdd(&cnt[lens[sy]], 1u);
+                __syncwarp();
+                if (lane == 0) {
+                    uint32_t code = 0, prev = 0;
+                    for (int b = 1; b < 16; b++) {
+                        code = (code + prev) << 1;
+                        prev = cnt[b];
+                        cnt[b] = code;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t base = 0; base < nsy; base += 32) {
+                    const uint32_t sy = base + lane;
+                    const uint32_t l = sy < nsy ? lens[sy] : 0u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, l ? l : 100u + lane);
+                    const uint32_t rank = __popc(peers & lt);
+                    const uint32_t before = l ? seen[l] : 0u;
+                    __syncwarp();
+                    if (l && rank == 0) seen[l] = before + __popc(peers);
+                    __syncwarp();
+                    if (sy < nsy) {
+                        s.codes[cbase + sy] = l ? (l << 16) | bitrev(cnt[l] + before + rank, (int)l) : 0u;
+                        const uint32_t f = g[cbase + sy];  // true counts (without the forced code)
+                        const uint32_t xb = tree ? (uint32_t)dsym_extra((int)sy) : (sy > 256 ? (uint32_t)lsym_extra((int)sy) : 0u);
+                        cd += f * (l + xb);
+                        cf += f * ((tree ? 5u : (uint32_t)fixed_lit_len((int)sy)) + xb);
+                    }
+                }
+                __syncwarp();
             }
             if (cd) atomicAdd(&s.cost_dyn, cd);
             if (cf) atomicAdd(&s.cost_fix, cf);
         }
+        __syncwarp();
+        if (lane == 0) plan_header_from_lengths(s.dh, s.hw);  // RLE + code-length code (serial, small)
         __syncwarp();
         if (lane == 0) {
             const uint64_t dyn_bits = (uint64_t)s.dh.bits + s.cost_dyn, fix_bits = 3ull + s.cost_fix;
@@ -1334,7 +1422,7 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
 }
 
 size_t parse_smem(uint32_t nmax, bool match_smem) {
-    return (size_t)nmax + 16 + 2 * (size_t)(nmax + nmax / 32) + CNT_WORDS * 4 + nmax / 32 + nmax / 8 +
+    return (size_t)nmax + 16 + 2 * (size_t)(nmax + nmax / 32) + CNT_WORDS * 4 + nmax / 16 +
            ((sizeof(ParseSm) + 15) & ~15u) + (match_smem ? 4 * (size_t)(nmax + nmax / 32) : 0) + 64;
 }
 
@@ -1416,8 +1504,8 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
 
     const size_t sm_parse[2] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_LARGE, false)};
     const size_t sm_huff = sizeof(HuffSm) * HUFF_WARPS;
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sm_parse[0] > sm_parse[1] ? sm_parse[0] : sm_parse[1])));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<RS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[0]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[1]));
     HMSE_CUDA(ctx, cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_huff));
     const uint32_t nmax_c[2] = {NMAX_SMALL, NMAX_LARGE};
     const uint32_t batch_c[2] = {BATCH_SMALL, BATCH_LARGE};
@@ -1532,7 +1620,8 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             a.counter = counters + ci++;
             const uint32_t jobs = a.job1 - a.job0;
             KL(ctx);
-            parse_kernel<<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            if (c == 0) parse_kernel<RS_SMALL><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            else parse_kernel<5><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
             if (level != 0) {
                 const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
                 KL(ctx);
@@ -1564,7 +1653,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             KL(ctx);
             long_dict_kernel<<<jobs < (uint32_t)ctx->sm_count ? jobs : (uint32_t)ctx->sm_count, 1024, 0, st>>>(a);
             KL(ctx);
-            parse_kernel<<<jobs < ctas_c[1] ? jobs : ctas_c[1], T_PARSE, sm_parse[1], st>>>(a);
+            parse_kernel<5><<<jobs < ctas_c[1] ? jobs : ctas_c[1], T_PARSE, sm_parse[1], st>>>(a);
             const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
             KL(ctx);
             huffman_kernel<<<hb < hmax ? hb : hmax, HUFF_WARPS * 32, sm_huff, st>>>(a);
