@@ -306,3 +306,28 @@ class ShardedIngest(Ingest):
         else:
             blob, offs = ctx.empty(0, torch.uint8), ctx.empty(1, torch.int64).zero_()
         return IngestResult(cuts, digests, canon, first.view(torch.bool), sel, blob, offs, entry, id_base)
+
+
+class ShardedSimilarity:
+    """MinHash / LSH over byte-range shards (BASELINE.json config 5): every rank signs its own chunks, the band
+    keys travel to the band's owner (band % world) with one all-to-all, and the owner sorts its bands over ALL
+    chunks of the stream - (band, key, global id) groups equal to oracle.buckets on the whole stream, band-sliced."""
+
+    def __init__(self, ctx: Context, cfg=None, group=None):
+        from .config import SimConfig
+        self.ctx, self.cfg, self.group = ctx, cfg or SimConfig(), group
+
+    def run(self, d: torch.Tensor, cuts: torch.Tensor, start0: int = 0):
+        """Returns (sig int32 [n, n_perm], keys int64 [n, bands], (band int32, key int64, id int64) of the owned bands)."""
+        import torch.distributed as dist
+        ctx = self.ctx
+        sig = ctx.minhash(d, cuts, self.cfg, start0)
+        keys = ctx.lsh_keys(sig, self.cfg)
+        owned, mine, _ = sharding.exchange_lsh(keys, self.group)
+        if owned.shape[0] == 0 or not mine:
+            e32, e64 = ctx.empty(0, torch.int32), ctx.empty(0, torch.int64)
+            return sig, keys, (e32, e64, e64.clone())
+        band, key, ids = ctx.lsh_buckets(owned.contiguous())
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        band = band * world + rank          # local column -> global band number
+        return sig, keys, (band, key, ids)

@@ -9,6 +9,11 @@ computed so that it can be exercised with torch.distributed/gloo on CPU:
                     with one all-to-all, the owner answers the smallest gid per digest with a
                     second all-to-all (north_star: "GPU hash table partitioned by digest prefix
                     with NCCL all-to-all over NVLink").
+* exchange_lsh       global LSH bucketing: band b is owned by rank b % world.  Every rank sends each owner the
+                    columns of its key matrix that the owner holds (one all-to-all); because shards are
+                    contiguous and global ids ascend with the rank, the rows arrive in global id order, so the
+                    owner's matrix [N_total][bands_owned] goes straight into the stable per-band sort
+                    (hmse_lsh_buckets) with id = row (north_star: "partitioned by ... band prefix").
 One process per GPU; `dev` is the device the collectives' tensors live on (cuda for NCCL, cpu
 for gloo)."""
 from __future__ import annotations
@@ -75,3 +80,31 @@ def exchange_dedup(records: torch.Tensor, counts: List[int], owner_resolve: Call
     answers = owner_resolve(recv, sum(recv_counts))
     back = all_to_all_bytes(answers.view(torch.uint8), recv_counts, counts, 8, group)
     return back.view(torch.int64)
+
+
+def owned_bands(bands: int, rank: int, world: int) -> List[int]:
+    """Bands owned by `rank`: b % world == rank."""
+    return list(range(rank, bands, world))
+
+
+def exchange_lsh(keys: torch.Tensor, group=None) -> Tuple[torch.Tensor, List[int], int]:
+    """keys: int64 [n_local, bands] (uint64 bit patterns) of this rank's chunks, in stream order.
+    Returns (owned int64 [N_total, len(my_bands)], my_bands, id_base): row g of `owned` holds the keys of global
+    chunk g for the bands this rank owns; id_base is the global id of this rank's first chunk."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = keys.device
+    n, bands = int(keys.shape[0]), int(keys.shape[1])
+    counts_all = _all_gather_i64(n, dev, group)
+    id_base = sum(counts_all[:rank])
+    n_total = sum(counts_all)
+    mine = owned_bands(bands, rank, world)
+    parts, send_counts = [], []
+    for o in range(world):
+        cols = keys[:, o::world].contiguous().view(-1)      # [n, bands_o] row-major
+        parts.append(cols)
+        send_counts.append(int(cols.numel()))
+    send = torch.cat(parts) if parts else keys.new_empty(0)
+    recv_counts = [c * len(mine) for c in counts_all]
+    recv = torch.empty(sum(recv_counts), dtype=keys.dtype, device=dev)
+    dist.all_to_all_single(recv, send, recv_counts, send_counts, group=group)
+    return recv.view(n_total, len(mine)) if mine else recv.view(n_total, 0), mine, id_base

@@ -31,12 +31,14 @@ n_avail = (total - rank * per) if eof else per + cfg.max_size
 d = gen.generate(n_avail, byte_off=rank * per)
 zd = ctx.stage(pc.zdict())
 res = hmse_b200.ShardedIngest(ctx, cfg, zd).run(d, per, eof)
+sig, keys, (lb, lk, li) = hmse_b200.ShardedSimilarity(ctx).run(d, res.cuts, start0=res.entry)
 torch.cuda.synchronize()
 out = dict(rank=rank, cuts=(res.cuts.cpu().numpy().view(np.uint64) + np.uint64(rank * per)).tolist(),
            canon=res.canon.cpu().numpy().tolist(), first=res.is_first.cpu().numpy().astype(int).tolist(),
            digests=res.digests.cpu().numpy().tobytes().hex(), id_base=res.id_base, entry=res.entry,
            blob=res.blob.cpu().numpy().tobytes().hex(), offs=res.offsets.cpu().numpy().tolist(),
-           sel=res.select.cpu().numpy().tolist())
+           sel=res.select.cpu().numpy().tolist(), keys=keys.cpu().numpy().view(np.uint64).tolist(),
+           lsh=[lb.cpu().numpy().tolist(), lk.cpu().numpy().view(np.uint64).tolist(), li.cpu().numpy().tolist()])
 json.dump(out, open(os.path.join(%r, "shard_%%d.json" %% rank), "w"))
 dist.destroy_process_group()
 '''
@@ -73,6 +75,16 @@ def test_two_gpu_sharded_ingest(tmp_path):
     wc, wf = oracle.dedup(want_dg)
     assert np.array_equal(np.array(sum((o["canon"] for o in outs), []), dtype=np.int64), wc)
     assert np.array_equal(np.array(sum((o["first"] for o in outs), []), dtype=bool), wf)
+    # LSH: band-partitioned buckets over the whole stream equal the oracle's, band by band
+    import importlib; om = importlib.import_module("oracle.minhash")
+    _, want_keys, (wb, wk, wi) = om.similarity(data, want_cuts, use_c=True)
+    keys = np.array(sum((o["keys"] for o in outs), []), dtype=np.uint64)
+    assert np.array_equal(keys, want_keys)
+    triples = sorted(zip(sum((o["lsh"][0] for o in outs), []), sum((o["lsh"][1] for o in outs), []),
+                         sum((o["lsh"][2] for o in outs), [])))
+    assert triples == list(zip(wb.tolist(), wk.tolist(), wi.tolist()))
+    for r, o in enumerate(outs):
+        assert set(o["lsh"][0]) <= set(range(r, 32, world))
     # every rank compressed exactly its globally-first chunks, and they inflate to the raw bytes
     zd = corpus.zdict()
     starts = np.concatenate([[0], want_cuts[:-1]]).astype(np.int64)

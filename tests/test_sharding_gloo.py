@@ -99,3 +99,47 @@ def test_stitch_and_dedup_over_gloo(world):
     assert [g[3] for g in got] == np.concatenate([[0], np.cumsum([len(g[1]) for g in got])[:-1]]).tolist()
     # rank 0 never re-resolves; later ranks re-resolve at most a few times
     assert got[0][5] == [0] and all(len(g[5]) <= 3 for g in got)
+
+
+def _lsh_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import importlib; om = importlib.import_module("oracle.minhash")
+        from hmse_b200 import sharding
+        rng = np.random.default_rng(77)
+        n_total, bands = 1000, 32
+        keys = rng.integers(0, 50, (n_total, bands)).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)  # many collisions
+        bounds = np.linspace(0, n_total, world + 1).astype(int)
+        if world == 3:
+            bounds[1] = bounds[0]     # a rank without chunks
+        lo, hi = bounds[rank], bounds[rank + 1]
+        local = torch.from_numpy(keys[lo:hi].view(np.int64).copy())
+        owned, mine, id_base = sharding.exchange_lsh(local)
+        assert id_base == lo and mine == list(range(rank, bands, world))
+        assert np.array_equal(owned.numpy().view(np.uint64), keys[:, rank::world])
+        b, k, i = om.buckets(owned.numpy().view(np.uint64))
+        q.put((rank, (b.astype(np.int64) * world + rank).tolist(), k.tolist(), i.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_lsh_band_exchange_over_gloo(world):
+    import importlib; om = importlib.import_module("oracle.minhash")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lsh_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(77)
+    keys = rng.integers(0, 50, (1000, 32)).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    wb, wk, wi = om.buckets(keys)
+    triples = sorted(zip(sum((g[1] for g in got), []), sum((g[2] for g in got), []), sum((g[3] for g in got), [])))
+    assert triples == list(zip(wb.tolist(), wk.tolist(), wi.tolist()))
