@@ -51,6 +51,7 @@ SIGNATURES = {
     "hmse_timing": (_I, [_P, _I]),
     "hmse_timing_ms": (_I, [_P, _I, C.POINTER(C.c_float)]),
     "hmse_launch_count": (_U64, [_P]),
+    "hmse_compress_stats": (_I, [_P, _PU64, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "hmse_dedup_partition": (_I, [_P, _P, _U64, _U64, _U32, _P, _P, _PU64, _P]),
     "hmse_dedup_records": (_I, [_P, _P, _U64, _P, _P]),
     "hmse_dedup_scatter": (_I, [_P, _P, _P, _U64, _U64, _P, _P, _P]),

@@ -33,6 +33,11 @@ HMSE_API int hmse_create(int device, hmse_ctx** out) {
             delete c;
             return HMSE_E_CUDA;
         }
+    for (int i = 0; i < 2 * HMSE_PARSE_EVENTS; i++)
+        if (cudaEventCreate(&c->pev[i]) != cudaSuccess) {
+            delete c;
+            return HMSE_E_CUDA;
+        }
     *out = c;
     return HMSE_OK;
 }
@@ -44,6 +49,8 @@ HMSE_API void hmse_destroy(hmse_ctx* ctx) {
         if (ctx->slot[i]) cudaFree(ctx->slot[i]);
     for (int i = 0; i < 2 * HT_COUNT; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2 * HMSE_PARSE_EVENTS; i++)
+        if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     free(ctx->dict_host);
     delete ctx;
@@ -118,3 +125,21 @@ HMSE_API int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms) {
 }
 
 HMSE_API uint64_t hmse_launch_count(hmse_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+HMSE_API int hmse_compress_stats(hmse_ctx* ctx, uint64_t* out4, float* parse_ms_sum, uint32_t* parse_ms_n) {
+    if (!ctx || !out4) return HMSE_E_INVAL;
+    for (int i = 0; i < 4; i++) out4[i] = ctx->stat[i];
+    float sum = 0.f;
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < ctx->pev_n && i < (uint32_t)HMSE_PARSE_EVENTS; i++) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->pev[2 * i + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms, ctx->pev[2 * i], ctx->pev[2 * i + 1]) != cudaSuccess)
+            HMSE_FAIL(ctx, HMSE_E_CUDA, "parse launch %u: event read failed", i);
+        sum += ms;
+        n++;
+    }
+    if (parse_ms_sum) *parse_ms_sum = sum;
+    if (parse_ms_n) *parse_ms_n = n;
+    return HMSE_OK;
+}

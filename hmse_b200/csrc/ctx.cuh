@@ -32,6 +32,7 @@ enum HmseSlot {
 };
 
 // Timed regions (hmse_timing_ms ids; also in include/hmse.h)
+constexpr int HMSE_PARSE_EVENTS = 128;
 enum HmseTimer {
     HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_COUNT
 };
@@ -58,6 +59,10 @@ struct hmse_ctx {
     uint64_t seg_len, n_seg, seg_cap;
     uint64_t res_n_own;
     int res_eof, res_valid;
+    // per-launch spans of the dominant kernel (parse_kernel) of the last hmse_compress, and what it moved
+    cudaEvent_t pev[2 * HMSE_PARSE_EVENTS];
+    uint32_t pev_n;
+    uint64_t stat[4];  // [0] parse launches, [1] token words written, [2] input bytes parsed, [3] chunks parsed
     uint64_t dedup_cap, dedup_n;  // streaming dedup table (hmse_dedup_begin / hmse_dedup_append)
     void* dict_host;  // host copy + checksum of the indexed preset dictionary (deflate.cu)
 };

@@ -109,6 +109,8 @@ struct DeflArgs {
 // Per-phase cycle counters of parse_kernel (thread 0 of every CTA, summed over chunks); read by
 // hmse_debug_deflate_prof.  A dozen clock reads per chunk: negligible.
 __device__ unsigned long long g_prof[16];
+// [0] token words, [1] input bytes, [2] chunks parsed since the host last cleared them (hmse_compress_stats)
+__device__ unsigned long long g_stat[4];
 #define PROF(i)                                                     \
     if (t == 0) {                                                   \
         const long long now__ = clock64();                          \
@@ -676,6 +678,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             rec.bits = 0;
             rec.pad = 0;
             a.recs[bj] = rec;
+            atomicAdd(&g_stat[0], (unsigned long long)n_words);
+            atomicAdd(&g_stat[1], (unsigned long long)n);
+            atomicAdd(&g_stat[2], 1ull);
         }
         PROF(8)
         if (t == 0) atomicAdd(&g_prof[15], 1ull);
@@ -1607,6 +1612,19 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         long_dicts = ldicts;
     }
 
+    // one event pair per parse launch (timing mode): the roofline of the dominant kernel is per launch
+    ctx->pev_n = 0;
+    uint32_t n_parse = 0;
+#define PARSE_EV(end)                                                                          \
+    if (ctx->timing && ctx->pev_n < (uint32_t)HMSE_PARSE_EVENTS) {                            \
+        cudaEventRecord(ctx->pev[2 * ctx->pev_n + (end)], st);                                \
+        if (end) ctx->pev_n++;                                                                \
+    }                                                                                          \
+    if (end) n_parse++
+    {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        HMSE_CUDA(ctx, cudaMemcpyToSymbolAsync(g_stat, z, sizeof(z), 0, cudaMemcpyHostToDevice, st));
+    }
     HT_BEGIN(ctx, HT_DEFLATE, st);
     uint32_t ci = 0;
     const uint32_t hmax = (uint32_t)ctx->sm_count * 3, emax = (uint32_t)ctx->sm_count * 8;
@@ -1620,8 +1638,10 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             a.counter = counters + ci++;
             const uint32_t jobs = a.job1 - a.job0;
             KL(ctx);
+            PARSE_EV(0);
             if (c == 0) parse_kernel<RS_SMALL><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
             else parse_kernel<5><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            PARSE_EV(1);
             if (level != 0) {
                 const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
                 KL(ctx);
@@ -1653,7 +1673,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             KL(ctx);
             long_dict_kernel<<<jobs < (uint32_t)ctx->sm_count ? jobs : (uint32_t)ctx->sm_count, 1024, 0, st>>>(a);
             KL(ctx);
+            PARSE_EV(0);
             parse_kernel<5><<<jobs < ctas_c[1] ? jobs : ctas_c[1], T_PARSE, sm_parse[1], st>>>(a);
+            PARSE_EV(1);
             const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
             KL(ctx);
             huffman_kernel<<<hb < hmax ? hb : hmax, HUFF_WARPS * 32, sm_huff, st>>>(a);
@@ -1681,8 +1703,17 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     rc = hmse_exclusive_scan_u64(ctx, sizes, d_offsets, m + 1, d_tot + 1, st);
     if (rc) return rc;
     if (int mrc = hmse_mail(ctx, 0, d_tot + 1, 2, st)) return mrc;
+    {
+        void* gs = nullptr;
+        HMSE_CUDA(ctx, cudaGetSymbolAddress(&gs, g_stat));
+        if (int mrc = hmse_mail(ctx, 8, gs, 6, st)) return mrc;
+    }
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     *total = mail[0];
+    ctx->stat[0] = n_parse;
+    ctx->stat[1] = mail[4];
+    ctx->stat[2] = mail[5];
+    ctx->stat[3] = mail[6];
     if (!d_out || mail[0] > out_cap)
         HMSE_FAIL(ctx, HMSE_E_CAPACITY, "d_out capacity %llu < %llu bytes", (unsigned long long)out_cap,
                   (unsigned long long)mail[0]);

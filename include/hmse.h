@@ -73,6 +73,11 @@ int hmse_timing(hmse_ctx* ctx, int enable);
 int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms);
 /* Kernels launched through this ctx since hmse_create. */
 uint64_t hmse_launch_count(hmse_ctx* ctx);
+/* Facts about the last hmse_compress for the roofline of its dominant kernel (parse_kernel):
+ * out4 = {parse launches, 16-bit token words written, input bytes parsed, chunks (blocks) parsed};
+ * with timing enabled, *parse_ms_sum / *parse_ms_n = summed CUDA-event spans of (at most the first 128)
+ * parse launches and how many were timed. */
+int hmse_compress_stats(hmse_ctx* ctx, uint64_t* out4, float* parse_ms_sum, uint32_t* parse_ms_n);
 
 /* ---- L2 chunking: replaces rabin_slide + the boundary loop of benchmark_fastcdc
  *      (README.md:2456-2464, 2475-2490). ------------------------------------------------- */
