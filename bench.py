@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--piece-mib", type=int, default=1024, help="piece size of the streaming end-to-end path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-size inflate + digest round-trip check")
     return ap.parse_args()
 
 
@@ -290,7 +291,6 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = (lib.hmse_launch_count(ctx.h) - launches0) // max(1, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    lib.hmse_timing(ctx.h, 0)
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
     value = total / (ms * 1e-3) / 1e9
 
@@ -333,11 +333,31 @@ def run_ours(args):
                 "pipeline_frac": ((total + sum_over_ranks(out_bytes) + 40 * sum_over_ranks(n_chunks)) / (ms * 1e-3) / 1e9)
                 / (peak * world)}
 
+    # ---- full-size parity property (not timed into `value`): every compressed stream of the last step goes
+    #      through the device read path (hmse_inflate) and the SHA-256 of what comes out must equal the digest
+    #      taken from the source chunk - an encode -> decode round trip plus a checksum of checksums ----
+    verify = None
+    if not args.no_verify:
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        bad, same = hmse_b200.verify_roundtrip(ctx, res, zd)
+        v1.record()
+        torch.cuda.synchronize()
+        f = C.c_float(0)
+        inf_ms = f.value if lib.hmse_timing_ms(ctx.h, 8, C.byref(f)) == 0 else None
+        verify = {"streams": int(sum_over_ranks(int(res.select.numel()))), "inflate_failed": int(sum_over_ranks(bad)),
+                  "digests_equal": bool(sum_over_ranks(0 if same else 1) == 0),
+                  "inflate_ms": inf_ms, "inflate_GBps_out": (sel_bytes / (inf_ms * 1e-3) / 1e9) if inf_ms else None,
+                  "total_ms": v0.elapsed_time(v1),
+                  "what": "hmse_inflate of every stream + SHA-256 of the output == digest of the source chunk, at full size"}
+
     uniq_chunks = sum_over_ranks(int(res.select.numel()))
     tot_chunks = sum_over_ranks(n_chunks)
     sel_b = sum_over_ranks(sel_bytes)
     out_b = sum_over_ranks(out_bytes)
 
+    lib.hmse_timing(ctx.h, 0)
     # ---- end to end: pinned host input -> device -> results back on the host, every step ----------
     e2e = None
     if not args.no_e2e:
@@ -415,7 +435,7 @@ def run_ours(args):
                            "chunks": int(tot_chunks), "unique_chunks": int(uniq_chunks),
                            "unique_bytes": int(sel_b), "compressed_bytes": int(out_b),
                            "compression_ratio_unique": (sel_b / out_b) if out_b else None},
-                "stages_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "stages_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "verify": verify, "gpu_launches": int(launches),
                 "clocks": clocks}
         print(json.dumps(line))
     if dist is not None:

@@ -182,6 +182,19 @@ class Context:
             return out[:total.value], offsets
         raise HmseError(_lib.HMSE_E_CAPACITY, "hmse_compress: capacity retry failed")
 
+    def inflate(self, blob: torch.Tensor, offsets: torch.Tensor, out_offsets: torch.Tensor, zdict: Optional[torch.Tensor]):
+        """(out uint8[out_offsets[-1]], status int32[m], n_bad): every stream inflated on the device."""
+        m = offsets.numel() - 1
+        total = int(out_offsets[-1]) if out_offsets.numel() else 0
+        out = self.empty(total + _PAD, torch.uint8)[:total]
+        status = self.empty(max(m, 1), torch.int32)[:m]
+        bad = C.c_uint64(0)
+        zp = zdict.data_ptr() if zdict is not None and zdict.numel() else None
+        zl = zdict.numel() if zdict is not None else 0
+        self.check(self.lib.hmse_inflate(self.h, blob.data_ptr(), offsets.data_ptr(), m, zp, zl, out.data_ptr(),
+                                         out_offsets.data_ptr(), status.data_ptr(), C.byref(bad), self.stream))
+        return out, status, int(bad.value)
+
     # -- L4 -------------------------------------------------------------------------------
     def minhash(self, d: torch.Tensor, cuts: torch.Tensor, cfg: SimConfig, start0: int = 0) -> torch.Tensor:
         m = cuts.numel()
@@ -262,6 +275,20 @@ def compress(data, cuts, select, zdict: bytes = b"", level: int = 6, start0: int
     zd = ctx.stage(zdict) if not isinstance(zdict, torch.Tensor) else zdict
     blob, offs = ctx.compress(d, ctx.stage_u64(cuts), sel, zd, level, start0)
     return (blob, offs) if dev else (blob.cpu().numpy(), _np_u64(offs))
+
+
+def inflate(blob, offsets, sizes, zdict: bytes = b"", ctx: Optional[Context] = None):
+    """The read path: (raw uint8[sum(sizes)], status int32[m]).  Stream j inflates to `sizes[j]` bytes at
+    offset sum(sizes[:j]); status[j] == 0 iff it is well formed and its Adler-32 (and DICTID) check out."""
+    ctx = ctx or default_context()
+    dev = _is_dev(blob)
+    b = ctx.stage(blob)
+    offs = ctx.stage_u64(offsets)
+    sz = np.ascontiguousarray(sizes.cpu().numpy() if isinstance(sizes, torch.Tensor) else sizes, dtype=np.uint64)
+    oo = np.concatenate([[np.uint64(0)], np.cumsum(sz, dtype=np.uint64)])
+    zd = ctx.stage(zdict) if not isinstance(zdict, torch.Tensor) else zdict
+    out, status, _ = ctx.inflate(b, offs, ctx.stage_u64(oo), zd)
+    return (out, status) if dev else (out.cpu().numpy(), status.cpu().numpy())
 
 
 def compress_bound(n: int) -> int:

@@ -27,6 +27,7 @@ enum HmseSlot {
     SLOT_MINHASH_MISC,  // work counter
     SLOT_LSH_SORT,      // radix-sort ping-pong buffers
     SLOT_LSH_MISC,      // digit histograms
+    SLOT_INFLATE_MISC,  // work counter, error count
     SLOT_CORPUS,
     SLOT_COUNT
 };
@@ -34,7 +35,7 @@ enum HmseSlot {
 // Timed regions (hmse_timing_ms ids; also in include/hmse.h)
 constexpr int HMSE_PARSE_EVENTS = 128;
 enum HmseTimer {
-    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_COUNT
+    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_INFLATE, HT_COUNT
 };
 
 struct hmse_ctx {

@@ -331,3 +331,20 @@ class ShardedSimilarity:
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         band = band * world + rank          # local column -> global band number
         return sig, keys, (band, key, ids)
+
+
+def verify_roundtrip(ctx: Context, res: IngestResult, zdict: torch.Tensor):
+    """The read path over a whole ingest result, on the device: every compressed stream is inflated
+    (hmse_inflate) and the SHA-256 of what comes out is compared with the digest taken from the source chunk at
+    ingest.  Returns (streams that failed to inflate, all digests equal)."""
+    sel = res.select
+    m = sel.numel()
+    if m == 0:
+        return 0, True
+    starts = torch.cat([torch.full((1,), res.entry, dtype=torch.int64, device=res.cuts.device), res.cuts[:-1]])
+    lens = (res.cuts - starts)[sel]
+    out_offs = torch.cat([torch.zeros(1, dtype=torch.int64, device=lens.device), torch.cumsum(lens, 0)])
+    out, status, bad = ctx.inflate(res.blob, res.offsets, out_offs, zdict)
+    dg = ctx.digest(out, out_offs[1:].contiguous())
+    same = bool(torch.equal(dg, res.digests[sel]))
+    return bad, same

@@ -69,6 +69,7 @@ uint64_t hmse_scratch_bytes(hmse_ctx* ctx);
 #define HMSE_T_PACK 5
 #define HMSE_T_MINHASH 6
 #define HMSE_T_LSH 7
+#define HMSE_T_INFLATE 8
 int hmse_timing(hmse_ctx* ctx, int enable);
 int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms);
 /* Kernels launched through this ctx since hmse_create. */
@@ -164,6 +165,18 @@ int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const u
 /* Diagnostic: cycles spent per encoder phase (thread 0 of each CTA, summed over chunks) since
  * the last reset; out16[15] = chunks encoded.  Host pointer. */
 int hmse_debug_deflate_prof(uint64_t* out16, int reset);
+
+/* ---- Read path: replaces mz_inflateInit2 / mz_inflate (README.md:2397-2400, 1638-1640). -------------
+ * Stream j = d_blob[d_offsets[j] : d_offsets[j+1]) is one RFC 1950 stream (any valid one with a window
+ * <= 32 KiB: the output of hmse_compress or of stock zlib with the same preset dictionary) and is inflated
+ * into d_out[d_out_offsets[j] : d_out_offsets[j+1]); the caller knows the raw sizes (the chunk index stores
+ * them, README.md:1264-1269).  d_status[j] = 0 when the stream is well formed, yields exactly that many bytes
+ * and its Adler-32 trailer (and DICTID, with a dictionary) agrees; otherwise an error code (1 header, 2 block
+ * header, 3 code / distance, 4 overrun, 5 length, 6 checksum) - a bad stream never writes outside its range.
+ * *n_bad (may be null) receives the number of non-zero statuses (synchronises `stream`). */
+int hmse_inflate(hmse_ctx* ctx, const uint8_t* d_blob, const uint64_t* d_offsets, uint64_t m,
+                 const uint8_t* d_zdict, uint32_t dict_len, uint8_t* d_out, const uint64_t* d_out_offsets,
+                 uint32_t* d_status, uint64_t* n_bad, void* stream);
 
 /* ---- L4 similarity: replaces minhash_compute (README.md:2578-2597) and LSH banding
  *      (README.md:2231-2235). -------------------------------------------------------------- */
