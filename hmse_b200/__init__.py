@@ -7,4 +7,4 @@ from .config import CDCConfig, SimConfig, gear_table, PAPER_MASK_S, PAPER_MASK_L
 from ._lib import HmseError, LIB_PATH, load as load_library  # noqa: F401
 from .api import Context, default_context, chunk, digest, dedup, compress, compress_bound, inflate, similarity  # noqa: F401
 from .ingest import Ingest, IngestStream, ShardedIngest, ShardedSimilarity, IngestResult, HostIngestResult, verify_roundtrip  # noqa: F401,E402
-from . import corpus, sharding  # noqa: F401,E402
+from . import archive, corpus, sharding  # noqa: F401,E402

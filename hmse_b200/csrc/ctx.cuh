@@ -28,6 +28,7 @@ enum HmseSlot {
     SLOT_LSH_SORT,      // radix-sort ping-pong buffers
     SLOT_LSH_MISC,      // digit histograms
     SLOT_INFLATE_MISC,  // work counter, error count
+    SLOT_ARCHIVE_MISC,  // slot map and reference counts of the index build
     SLOT_CORPUS,
     SLOT_COUNT
 };

@@ -178,6 +178,20 @@ int hmse_inflate(hmse_ctx* ctx, const uint8_t* d_blob, const uint64_t* d_offsets
                  const uint8_t* d_zdict, uint32_t dict_len, uint8_t* d_out, const uint64_t* d_out_offsets,
                  uint32_t* d_status, uint64_t* n_bad, void* stream);
 
+/* ---- Archive records (README.md:1264-1269 ChunkIndex, 1312 pointer records) and stream reassembly. ------
+ * d_index[k] (40 B, packed) = { sha256 of unique chunk k = chunk d_select[k], u32 lba = d_offsets[k] >> 9,
+ * u16 length = compressed bytes, u16 refcount (saturating) }; d_pointers[i] (8 B) = { u32 lba, u16 d_offsets[s] & 511,
+ * u16 raw length - 1 } with s the unique chunk that chunk i resolves to (d_canon[i] - id_base is its local index).
+ * Fails with HMSE_E_INVAL when a chunk is empty or longer than 65536 bytes, a compressed chunk is longer than
+ * 65535 bytes, or the store exceeds 2 TiB.  Synchronises `stream`. */
+int hmse_index_build(hmse_ctx* ctx, const uint8_t* d_digests, const int64_t* d_canon, uint64_t id_base,
+                     const uint64_t* d_cuts, uint64_t start0, uint64_t n, const uint64_t* d_select, uint64_t m,
+                     const uint64_t* d_offsets, uint8_t* d_index, uint8_t* d_pointers, void* stream);
+/* d_dst[d_dst_off[i] : d_dst_off[i+1]) = d_src[d_src_off[i] : + the same length) for i < n (d_dst_off has n+1
+ * entries, d_src_off n; d_src needs 4 readable bytes after its last segment). */
+int hmse_segment_copy(hmse_ctx* ctx, const uint8_t* d_src, const uint64_t* d_src_off, uint8_t* d_dst,
+                      const uint64_t* d_dst_off, uint64_t n, void* stream);
+
 /* ---- L4 similarity: replaces minhash_compute (README.md:2578-2597) and LSH banding
  *      (README.md:2231-2235). -------------------------------------------------------------- */
 

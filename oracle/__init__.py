@@ -33,4 +33,4 @@ from .sha import digest, dedup  # noqa: F401
 from .deflate import compress, inflate_all, make_zdict  # noqa: F401
 from .minhash import (murmur3_32, minhash, minhash_c, band_keys, buckets,  # noqa: F401
                       similarity)
-from . import corpus  # noqa: F401
+from . import archive, corpus  # noqa: F401

@@ -1,0 +1,76 @@
+"""Archive container (hmse_b200/archive.py): the device-built ChunkIndex entries and pointer records equal the
+oracle's restatement byte for byte; an archive restores to the input both through the device read path and through
+the pure zlib walker of the oracle; damaged archives are rejected."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def _ingest(ctx, data, zd):
+    import hmse_b200
+    return hmse_b200.Ingest(ctx, hmse_b200.CDCConfig(), zd).run(ctx.stage(data))
+
+
+def test_records_equal_oracle_and_roundtrip(ctx, corpus8, tmp_path):
+    import hmse_b200
+    from hmse_b200 import archive
+    zd = corpus.zdict()
+    data = np.concatenate([corpus8[:3 << 20], corpus8[1 << 20:2 << 20], corpus8[:1 << 20]])   # plenty of repeats
+    r = _ingest(ctx, data, zd)
+    ar = archive.build(r, zd, ctx=ctx)
+    cuts = r.cuts.cpu().numpy().view(np.uint64)
+    idx, ptr = oracle.archive.records(r.digests.cpu().numpy(), r.canon.cpu().numpy(), cuts, r.select.cpu().numpy(),
+                                      r.offsets.cpu().numpy().view(np.uint64))
+    assert np.array_equal(ar.index, idx) and np.array_equal(ar.pointers, ptr)
+    assert int(ar.index[:, 38:40].copy().view("<u2").max()) >= 2            # duplicates are reference counted
+    buf = ar.tobytes()
+    assert buf == oracle.archive.pack(zd, idx, ptr, r.blob.cpu().numpy(), data.size)
+    assert len(buf) < data.size // 3
+    # file round trip, device read path, and the zlib-only walker
+    path = tmp_path / "a.hmse"
+    ar.save(str(path))
+    back = archive.Archive.load(str(path))
+    assert archive.restore(back, ctx=ctx).tobytes() == data.tobytes()
+    assert oracle.archive.restore(buf) == data.tobytes()
+
+
+def test_archive_from_stream_and_small_inputs(ctx, corpus8):
+    import torch
+    import hmse_b200
+    from hmse_b200 import archive
+    zd = corpus.zdict()
+    st = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=512 << 10)
+    data = corpus8[:(2 << 20) + 777]
+    h = st.run(torch.from_numpy(data.copy()).pin_memory())
+    ar = archive.build(h, zd, ctx=ctx)
+    assert archive.restore(ar, ctx=ctx).tobytes() == data.tobytes()
+    for n in (1, 2047, 5000):
+        d = corpus8[:n]
+        ar = archive.build(_ingest(ctx, d, b""), b"", ctx=ctx)
+        assert ar.n_chunks == oracle.chunk(d).size
+        assert archive.restore(archive.Archive.frombytes(ar.tobytes()), ctx=ctx).tobytes() == d.tobytes()
+
+
+def test_damaged_archives_are_rejected(ctx, corpus8):
+    from hmse_b200 import archive
+    zd = corpus.zdict()
+    data = corpus8[:1 << 20]
+    ar = archive.build(_ingest(ctx, data, zd), zd, ctx=ctx)
+    buf = bytearray(ar.tobytes())
+    bad = bytearray(buf)
+    bad[-100] ^= 0xFF                                   # inside the last stored chunk
+    with pytest.raises(ValueError):
+        archive.restore(archive.Archive.frombytes(bytes(bad)), ctx=ctx)
+    bad = bytearray(buf)
+    o = 64 + len(zd) + ((-len(zd)) % 8) + ar.n_unique * 40
+    bad[o + 4] ^= 1                                     # a pointer record's in-sector offset
+    with pytest.raises(ValueError):
+        archive.restore(archive.Archive.frombytes(bytes(bad)), ctx=ctx)
+    with pytest.raises(ValueError):
+        archive.Archive.frombytes(bytes(buf[:-1]))
+    with pytest.raises(ValueError):
+        archive.Archive.frombytes(b"XXXXXXXX" + bytes(buf[8:]))

@@ -236,3 +236,30 @@ def test_compression_ratio_with_dictionary_beats_without():
     with_d, _ = oracle.compress(d, cuts, sel, corpus.zdict())
     without, _ = oracle.compress(d, cuts, sel, b"")
     assert with_d.size < 0.8 * without.size and d.size / with_d.size >= 2.5      # README.md:2417-2420 ratio >= 2.5
+
+
+def test_archive_records_and_pure_zlib_restore():
+    # oracle/archive.py against hand-checked field values and a zlib-only round trip
+    import zlib
+    from oracle import archive
+    zd = corpus.zdict()
+    data = corpus.generate(600000)
+    data = np.concatenate([data, data[:200000]])
+    cuts = oracle.chunk(data)
+    dg = oracle.digest(data, cuts)
+    canon, first = oracle.dedup(dg)
+    sel = np.flatnonzero(first)
+    blob, offs = oracle.compress(data, cuts, sel, zd)
+    idx, ptr = archive.records(dg, canon, cuts, sel, offs)
+    assert idx.shape == (sel.size, 40) and ptr.shape == (cuts.size, 8)
+    k = 3
+    assert idx[k, :32].tobytes() == dg[sel[k]].tobytes()
+    assert int.from_bytes(idx[k, 32:36].tobytes(), "little") == int(offs[k]) >> 9
+    assert int.from_bytes(idx[k, 36:38].tobytes(), "little") == int(offs[k + 1] - offs[k])
+    assert int.from_bytes(idx[k, 38:40].tobytes(), "little") == int((canon == sel[k]).sum())
+    i = int(np.flatnonzero(~first)[0])                       # a duplicate points at its first occurrence
+    s = int(np.searchsorted(sel, canon[i]))
+    assert int.from_bytes(ptr[i, 0:4].tobytes(), "little") * 512 + int.from_bytes(ptr[i, 4:6].tobytes(), "little") == int(offs[s])
+    assert int.from_bytes(ptr[i, 6:8].tobytes(), "little") + 1 == int(cuts[i] - cuts[i - 1])
+    buf = archive.pack(zd, idx, ptr, blob, data.size)
+    assert buf[:8] == b"HMSEARC1" and archive.restore(buf) == data.tobytes()
