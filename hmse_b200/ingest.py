@@ -85,14 +85,23 @@ class IngestStream(Ingest):
     """Host-to-host ingest of one stream in pieces (the spec's Core 0 I/O stage feeding the
     pipeline, README.md:141-145): piece k+1 is copied host->device while piece k is chunked,
     hashed, deduplicated against everything seen so far (hmse_dedup_begin/append) and
-    compressed, and the results of piece k-1 travel device->host - three CUDA streams.
+    compressed, and the results of piece k-1 travel device->host - three CUDA streams (four with `overlap`: the
+    chunking, hashing and deduplication of piece k+1 then run on their own stream, host thread and hmse_ctx beside the
+    compression of piece k).
     A chunk that straddles a piece boundary is resolved with the next piece (the boundary rule of
     hmse_chunk_resolve), so cuts, digests, canon and streams equal the one-shot `Ingest.run`.
     Pieces grow from piece_bytes/16 to piece_bytes and shrink again at the end of the stream: the
     first kernels start after a short copy and little is left to copy out after the last one."""
 
-    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, piece_bytes: int = 1 << 30):
+    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, piece_bytes: int = 1 << 30,
+                 overlap: bool = False):
         super().__init__(ctx, cdc, zdict, level)
+        # overlap: run the front stage (cuts, digests, dedup) of the next piece on its own thread/stream/ctx beside the
+        # compression.  Measured on B200: no gain (152.0 -> 151.3 ms per 4 GB) - the persistent parse CTAs hold every
+        # SM's registers, so the front kernels only run where the compression kernels would have; off by default.
+        self.overlap = overlap
+        self.ctx2 = None           # second hmse_ctx (own scratch and mailbox) for the compression side when overlapping
+        self.s_front = None
         if piece_bytes % 16 or piece_bytes < 4 * cdc.max_size:
             raise ValueError("piece_bytes must be a multiple of 16 and >= 4 * max_size")
         self.piece = int(piece_bytes)
@@ -153,6 +162,8 @@ class IngestStream(Ingest):
         return cap_chunks, h
 
     def run(self, host_in: torch.Tensor, host_blob_cap: Optional[int] = None, compress: bool = True) -> HostIngestResult:
+        import queue
+        import threading
         import time
         ctx, cfg = self.ctx, self.cdc
         if host_in.is_cuda or host_in.dtype != torch.uint8 or host_in.dim() != 1:
@@ -169,6 +180,7 @@ class IngestStream(Ingest):
         dbuf, dig = self._dbuf, self._dig
         cur = torch.cuda.current_stream(ctx.device)
         ends = self.schedule(n) if n else [0]
+        overlap = self.overlap and compress and len(ends) > 1
         # every host->device copy is queued up front: the copy engine runs ahead of the kernels
         self.s_h2d.wait_stream(cur)
         ev_in = []
@@ -182,78 +194,149 @@ class IngestStream(Ingest):
                 ev_in.append(e)
                 a = b
         mark("copies queued")
-        ctx.check(ctx.lib.hmse_dedup_begin(ctx.h, cap_chunks, ctx.stream))
         host["offsets"][0] = 0
+
+        def front(stream):
+            """Pieces through scan, resolve, SHA-256, streaming dedup and selection, on `stream` with self.ctx."""
+            ctx.check(ctx.lib.hmse_dedup_begin(ctx.h, cap_chunks, ctx.stream))
+            entry = 0                  # absolute offset of the first chunk not yet cut
+            n0 = 0                     # chunks before this piece
+            for k, end in enumerate(ends):
+                stream.wait_event(ev_in[k])
+                eof = k == len(ends) - 1
+                base = entry & ~15
+                view = dbuf[base:end]
+                n_own = end - base if eof else end - base - cfg.max_size
+                if n_own <= entry - base:
+                    continue           # (only when a piece is tiny) nothing can be decided yet
+                mark("piece %d start" % k)
+                ctx.chunk_scan(view, cfg)
+                cuts, exit_off = ctx.chunk_resolve(view, cfg, n_own, eof, entry - base)
+                mark("piece %d cuts" % k)
+                nk = cuts.numel()
+                if nk == 0:
+                    continue
+                dg = dig[n0 * 32:(n0 + nk) * 32]
+                ctx.check(ctx.lib.hmse_digest(ctx.h, view.data_ptr(), entry - base, cuts.data_ptr(), nk, dg.data_ptr(),
+                                              ctx.stream))
+                canon = ctx.empty(nk, torch.int64)
+                first = ctx.empty(nk, torch.uint8)
+                ctx.check(ctx.lib.hmse_dedup_append(ctx.h, dig.data_ptr(), n0, nk, canon.data_ptr(), first.data_ptr(),
+                                                    ctx.stream))
+                sel = self.select_first(first) if compress else None
+                cuts_abs = cuts + base
+                mark("piece %d dedup" % k)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                yield dict(k=k, view=view, start0=entry - base, cuts=cuts, cuts_abs=cuts_abs, nk=nk, n0=n0, dg=dg, canon=canon,
+                           first=first, sel=sel, ev=ev)
+                n0 += nk
+                entry = base + exit_off
+
+        if overlap:
+            # the front stage of piece k+1 runs on its own thread, stream and hmse_ctx while piece k is compressed:
+            # its kernels fill the gaps between the compression kernels, its host round trips cost nothing
+            if self.ctx2 is None:
+                self.ctx2 = Context(ctx.device)
+                self.s_front = torch.cuda.Stream(ctx.tdev)
+            self.s_front.wait_stream(cur)
+            q: "queue.Queue" = queue.Queue(maxsize=2)
+            stop = threading.Event()
+
+            def put(item):
+                while not stop.is_set():
+                    try:
+                        q.put(item, timeout=0.1)
+                        return
+                    except queue.Full:
+                        pass
+
+            def worker():
+                try:
+                    torch.cuda.set_device(ctx.device)
+                    with torch.cuda.stream(self.s_front):
+                        for rec in front(self.s_front):
+                            put(rec)
+                            if stop.is_set():
+                                return
+                    put(None)
+                except BaseException as e:  # noqa: BLE001 - handed to the caller's thread
+                    put(e)
+
+            th = threading.Thread(target=worker, daemon=True)
+            th.start()
+
+            def records():
+                while True:
+                    item = q.get()
+                    if item is None:
+                        return
+                    if isinstance(item, BaseException):
+                        raise item
+                    yield item
+            back = self.ctx2
+        else:
+            stop, th = None, None
+            records = lambda: front(cur)  # noqa: E731
+            back = ctx
+
         keep = []                      # small device results stay referenced until the copies out have run
         ev_out = [None, None]          # copy-out of the piece that last used stage buffer j
-        entry = 0                      # absolute offset of the first chunk not yet cut
         n_chunks = m_total = blob_total = 0
         d2h = 0
-        for k, end in enumerate(ends):
-            cur.wait_event(ev_in[k])
-            eof = k == len(ends) - 1
-            base = entry & ~15
-            view = dbuf[base:end]
-            n_own = end - base if eof else end - base - cfg.max_size
-            if n_own <= entry - base:
-                continue               # (only when a piece is tiny) nothing can be decided yet
-            mark("piece %d start" % k)
-            ctx.chunk_scan(view, cfg)
-            cuts, exit_off = ctx.chunk_resolve(view, cfg, n_own, eof, entry - base)
-            mark("piece %d cuts" % k)
-            nk = cuts.numel()
-            if nk == 0:
-                continue
-            dg = dig[n_chunks * 32:(n_chunks + nk) * 32]
-            ctx.check(ctx.lib.hmse_digest(ctx.h, view.data_ptr(), entry - base, cuts.data_ptr(), nk, dg.data_ptr(), ctx.stream))
-            canon = ctx.empty(nk, torch.int64)
-            first = ctx.empty(nk, torch.uint8)
-            ctx.check(ctx.lib.hmse_dedup_append(ctx.h, dig.data_ptr(), n_chunks, nk, canon.data_ptr(), first.data_ptr(),
-                                                ctx.stream))
-            mk = bk = 0
-            if compress:
-                sel = self.select_first(first)
-                mark("piece %d dedup" % k)
-                j = k & 1
-                want = (end - base) // 2 + (1 << 20)
-                if self._stage[j] is None or self._stage[j].numel() < want:
-                    self._stage[j] = None
-                    self._stage[j] = ctx.empty(want, torch.uint8)
-                if ev_out[j] is not None:
-                    cur.wait_event(ev_out[j])      # the buffer's previous contents have left the device
-                blob, offs = ctx.compress(view, cuts, sel, self.zdict, self.level, start0=entry - base, out=self._stage[j])
-                if blob.data_ptr() != self._stage[j].data_ptr():   # did not fit (poorly compressible piece): keep the larger one
-                    self._stage[j] = blob
-                mk, bk = sel.numel(), blob.numel()
-                if blob_total + bk > host["blob"].numel():
-                    raise ValueError("host_blob_cap %d is too small" % host["blob"].numel())
-                offs_abs = offs[1:] + blob_total
-            cuts_abs = cuts + base
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self.s_d2h.wait_event(ev)
-            with torch.cuda.stream(self.s_d2h):
-                host["cuts"][n_chunks:n_chunks + nk].copy_(cuts_abs, non_blocking=True)
-                host["digests"][n_chunks * 32:(n_chunks + nk) * 32].copy_(dg, non_blocking=True)
-                host["canon"][n_chunks:n_chunks + nk].copy_(canon, non_blocking=True)
-                d2h += nk * 48
-                if mk:
-                    host["offsets"][1 + m_total:1 + m_total + mk].copy_(offs_abs, non_blocking=True)
-                    host["blob"][blob_total:blob_total + bk].copy_(blob, non_blocking=True)
-                    d2h += mk * 8 + bk
-                    keep.append(offs_abs)
-                    ev_out[k & 1] = torch.cuda.Event()
-                    ev_out[k & 1].record(self.s_d2h)
-            keep += [cuts_abs, canon]
-            if self.timing_hook is not None:
-                torch.cuda.current_stream(ctx.device).synchronize()
-                self.timing_hook()
-            n_chunks += nk
-            m_total += mk
-            blob_total += bk
-            entry = base + exit_off
+        try:
+            for rec in records():
+                k, nk = rec["k"], rec["nk"]
+                cur.wait_event(rec["ev"])
+                mk = bk = 0
+                if compress:
+                    j = k & 1
+                    want = rec["view"].numel() // 2 + (1 << 20)
+                    if self._stage[j] is None or self._stage[j].numel() < want:
+                        self._stage[j] = None
+                        self._stage[j] = back.empty(want, torch.uint8)
+                    if ev_out[j] is not None:
+                        cur.wait_event(ev_out[j])      # the buffer's previous contents have left the device
+                    blob, offs = back.compress(rec["view"], rec["cuts"], rec["sel"], self.zdict, self.level,
+                                               start0=rec["start0"], out=self._stage[j])
+                    if blob.data_ptr() != self._stage[j].data_ptr():   # did not fit (poorly compressible): keep the larger one
+                        self._stage[j] = blob
+                    mk, bk = rec["sel"].numel(), blob.numel()
+                    if blob_total + bk > host["blob"].numel():
+                        raise ValueError("host_blob_cap %d is too small" % host["blob"].numel())
+                    offs_abs = offs[1:] + blob_total
+                    mark("piece %d compressed" % k)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.s_d2h.wait_event(ev)
+                with torch.cuda.stream(self.s_d2h):
+                    host["cuts"][n_chunks:n_chunks + nk].copy_(rec["cuts_abs"], non_blocking=True)
+                    host["digests"][n_chunks * 32:(n_chunks + nk) * 32].copy_(rec["dg"], non_blocking=True)
+                    host["canon"][n_chunks:n_chunks + nk].copy_(rec["canon"], non_blocking=True)
+                    d2h += nk * 48
+                    if mk:
+                        host["offsets"][1 + m_total:1 + m_total + mk].copy_(offs_abs, non_blocking=True)
+                        host["blob"][blob_total:blob_total + bk].copy_(blob, non_blocking=True)
+                        d2h += mk * 8 + bk
+                        keep.append(offs_abs)
+                        ev_out[k & 1] = torch.cuda.Event()
+                        ev_out[k & 1].record(self.s_d2h)
+                keep.append(rec)
+                if self.timing_hook is not None and not overlap:
+                    torch.cuda.current_stream(ctx.device).synchronize()
+                    self.timing_hook()
+                assert rec["n0"] == n_chunks
+                n_chunks += nk
+                m_total += mk
+                blob_total += bk
+        finally:
+            if stop is not None:
+                stop.set()
+                th.join(timeout=30)
         mark("last piece queued")
         cur.wait_stream(self.s_d2h)    # the caller's stream (and its events) see the whole job
+        if overlap:
+            cur.wait_stream(self.s_front)
         torch.cuda.current_stream(ctx.device).synchronize()
         mark("done")
         del keep

@@ -16,8 +16,9 @@ def _one_shot(ctx, data, zd):
     return r
 
 
+@pytest.mark.parametrize("overlap", [True, False])
 @pytest.mark.parametrize("piece_kib", [128, 1024, 3000, 1 << 14])
-def test_stream_equals_one_shot_and_oracle(ctx, corpus8, piece_kib):
+def test_stream_equals_one_shot_and_oracle(ctx, corpus8, piece_kib, overlap):
     import torch
     import hmse_b200
     import oracle
@@ -25,7 +26,7 @@ def test_stream_equals_one_shot_and_oracle(ctx, corpus8, piece_kib):
     zd = corpus.zdict()
     data = corpus8[:6 * (1 << 20) + 12345]
     host = torch.from_numpy(data.copy()).pin_memory()
-    st = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=(piece_kib << 10) & ~15)
+    st = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=(piece_kib << 10) & ~15, overlap=overlap)
     for _ in range(2):  # second run reuses every buffer and a cleared table
         h = st.run(host)
     r = _one_shot(ctx, data, zd)

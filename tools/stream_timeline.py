@@ -34,7 +34,7 @@ def main():
     a.record(); hb.copy_(r.blob, non_blocking=True); b.record(); torch.cuda.synchronize()
     print("D2H %.1f GB/s (%d MB)" % (hb.numel() / a.elapsed_time(b) / 1e6, hb.numel() >> 20))
     del r, d
-    st = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=piece << 20)
+    st = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=piece << 20, overlap=len(sys.argv) > 3)
     st.trace = []
     for _ in range(3):
         st.trace = []
