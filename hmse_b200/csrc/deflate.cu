@@ -694,13 +694,182 @@ struct HuffSm {
     uint32_t freq[REC_WORDS];
     uint32_t codes[REC_WORDS];
     HuffWork hw;
-    HuffWorkSmall hw2;
     DynHeader dh;
-    uint8_t hdr[640];
+    uint32_t hdr[160];     // dynamic header bits
     uint32_t bl32[16];
+    uint32_t small[32];    // per-length running counts / code-length-code frequencies
     uint32_t n_used, cost_dyn, cost_fix, mode, hdr_bits, bits;
     unsigned long long kraft;
 };
+
+// ---- warp-collective pieces of the Huffman construction -------------------------------------------------
+
+// Code lengths of one tree whose k >= 2 leaves lie sorted ascending by (freq, symbol) in hw.w[0..k) / hw.order[0..k).
+// The caller has zeroed lens[] for the unused symbols.  Two-queue merge on lane 0, everything else lane-parallel;
+// depth overflow is repaired on the per-length histogram like zlib's gen_bitlen.
+__device__ void warp_tree_lengths(HuffWork& hw, uint32_t k, int maxbits, uint8_t* lens, uint32_t* bl32,
+                                  unsigned long long* kraft, unsigned lane) {
+    if (lane < 16) bl32[lane] = 0;
+    if (lane == 0) {
+        *kraft = 0;
+        huff_merge(hw, (int)k);
+    }
+    __syncwarp();
+    const uint32_t root = 2 * k - 2;
+    for (uint32_t i = lane; i < k; i += 32) {
+        uint32_t node = i, dpt = 0;
+        while (node != root) {
+            node = hw.parent[node];
+            dpt++;
+        }
+        if (dpt > (uint32_t)maxbits) dpt = (uint32_t)maxbits;
+        atomicAdd(&bl32[dpt], 1u);
+        atomicAdd(kraft, 1ull << (maxbits - dpt));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int b = 0; b < 16; b++) hw.bl_count[b] = (uint16_t)bl32[b];
+        huff_fix_overflow(hw.bl_count, maxbits, *kraft);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < k; i += 32) {  // rarest leaves take the longest codes
+        uint32_t cum = 0, L = 1;
+        for (int bits = maxbits; bits >= 1; bits--) {
+            cum += hw.bl_count[bits];
+            if (i < cum) {
+                L = (uint32_t)bits;
+                break;
+            }
+        }
+        lens[hw.order[i]] = (uint8_t)L;
+    }
+    __syncwarp();
+}
+
+// Leaves of an alphabet of at most 32 symbols (lane = symbol, f = its count, 0 beyond the alphabet) sorted into
+// hw.w / hw.order by (freq, symbol); at least two codes are forced like zlib's build_tree.  Returns the leaf count.
+__device__ uint32_t warp_sort_small(uint32_t f, HuffWork& hw, unsigned lane) {
+    uint32_t used = __ballot_sync(0xffffffffu, f != 0);
+    if (__popc(used) < 2) {
+        if (used == 0) {
+            if (lane < 2) f = 1;
+        } else if (used & 1u) {
+            if (lane == 1) f = 1;
+        } else if (lane == 0) {
+            f = 1;
+        }
+        used = __ballot_sync(0xffffffffu, f != 0);
+    }
+    uint32_t rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t fj = __shfl_sync(0xffffffffu, f, j);
+        rank += (fj != 0) && (fj < f || (fj == f && (unsigned)j < lane));
+    }
+    if (f) {
+        hw.w[rank] = f;
+        hw.order[rank] = (uint16_t)lane;
+    }
+    __syncwarp();
+    return (uint32_t)__popc(used);
+}
+
+// zlib's run-length coding of one tree's code lengths (scan_tree / send_tree, rle_lengths in deflate_core.h), position
+// parallel: every position learns the start and the end of its run (two passes over the 32-wide slices, forwards and
+// backwards) and decides by itself whether an entry begins there.  out[base..) receives sym | extra << 8 in order;
+// returns the entry count.  ts / te: n u16 of scratch each.
+__device__ uint32_t warp_rle(const uint8_t* lens, uint32_t n, uint16_t* out, uint32_t out_base, uint16_t* ts, uint16_t* te,
+                             unsigned lane) {
+    const uint32_t upto = lane == 31 ? 0xffffffffu : (2u << lane) - 1;   // lanes 0 .. lane
+    const uint32_t nslices = (n + 31) >> 5;
+    uint32_t carry = 0;
+    for (uint32_t sl = 0; sl < nslices; sl++) {
+        const uint32_t base = sl << 5, i = base + lane;
+        const uint32_t v = i < n ? lens[i] : 0x1FFu;
+        uint32_t vp = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) vp = base ? lens[base - 1] : 0x2FFu;
+        const uint32_t hm = __ballot_sync(0xffffffffu, i < n && v != vp);
+        const uint32_t m = hm & upto;
+        const uint32_t st = m ? base + 31 - (uint32_t)__clz((int)m) : carry;
+        if (i < n) ts[i] = (uint16_t)st;
+        carry = __shfl_sync(0xffffffffu, st, 31);
+    }
+    uint32_t carry_e = n;
+    for (uint32_t sl = nslices; sl-- > 0;) {
+        const uint32_t base = sl << 5, i = base + lane;
+        const uint32_t v = i < n ? lens[i] : 0x1FFu;
+        uint32_t vp = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) vp = base ? lens[base - 1] : 0x2FFu;
+        const uint32_t hm = __ballot_sync(0xffffffffu, i < n && v != vp);
+        const uint32_t m = hm & ~upto;
+        if (i < n) te[i] = (uint16_t)(m ? base + (uint32_t)__ffs((int)m) - 1 : carry_e);
+        if (hm) carry_e = base + (uint32_t)__ffs((int)hm) - 1;
+    }
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1;
+    uint32_t count = 0;
+    for (uint32_t sl = 0; sl < nslices; sl++) {
+        const uint32_t i = (sl << 5) + lane;
+        bool emit = false;
+        uint32_t entry = 0;
+        if (i < n) {
+            const uint32_t v = lens[i], st = ts[i], r = te[i] - st, o = i - st;
+            if (v == 0) {   // full 138-runs, then 18 / 17 / up to two literal zeros
+                const uint32_t full = r / 138, rem = r - 138 * full;
+                if (o < 138 * full) {
+                    emit = o % 138 == 0;
+                    entry = 18u | ((138u - 11u) << 8);
+                } else if (rem >= 11) {
+                    emit = o == 138 * full;
+                    entry = 18u | ((rem - 11u) << 8);
+                } else if (rem >= 3) {
+                    emit = o == 138 * full;
+                    entry = 17u | ((rem - 3u) << 8);
+                } else {
+                    emit = true;
+                    entry = 0;
+                }
+            } else if (o == 0) {   // the length itself, then repeats of 6, then 16 / up to two literals
+                emit = true;
+                entry = v;
+            } else {
+                const uint32_t R = r - 1, o1 = o - 1, full = R / 6, rem = R - 6 * full;
+                if (o1 < 6 * full) {
+                    emit = o1 % 6 == 0;
+                    entry = 16u | (3u << 8);
+                } else if (rem >= 3) {
+                    emit = o1 == 6 * full;
+                    entry = 16u | ((rem - 3u) << 8);
+                } else {
+                    emit = true;
+                    entry = v;
+                }
+            }
+        }
+        const uint32_t bm = __ballot_sync(0xffffffffu, emit);
+        if (emit) out[out_base + count + __popc(bm & lt)] = (uint16_t)entry;
+        count += __popc(bm);
+    }
+    __syncwarp();
+    return count;
+}
+
+// Appends (val, nb <= 17) entries to a zeroed bit string of 32-bit words, 32 entries per call in lane order;
+// `bitpos` is the running length (warp-uniform).
+__device__ __forceinline__ void warp_put_bits(uint32_t* words, uint32_t& bitpos, uint32_t val, uint32_t nb, unsigned lane) {
+    uint32_t inc = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    const uint32_t off = bitpos + inc - nb;
+    if (nb) {
+        atomicOr(&words[off >> 5], val << (off & 31));
+        if ((off & 31) + nb > 32) atomicOr(&words[(off >> 5) + 1], val >> (32 - (off & 31)));
+    }
+    bitpos += __shfl_sync(0xffffffffu, inc, 31);
+}
 
 __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -797,49 +966,19 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
             for (uint32_t i = lane; i < REC_WORDS; i += 32) s.codes[i] = 0;   // the sort borrowed them
         }
         __syncwarp();
-        if (lane == 0) huff_merge(s.hw, (int)k_used);
-        if (lane == 1) {  // the distance tree is small: one lane, concurrently with the merge
-            uint32_t df[32];
-            for (int q = 0; q < 32; q++) df[q] = s.freq[288 + q];
-            build_lengths(df, NDIST, 15, s.dh.dist_lens, s.hw2);
+        // literal/length tree, then the distance tree (30 symbols: one per lane)
+        warp_tree_lengths(s.hw, k_used, 15, s.dh.lit_lens, s.bl32, &s.kraft, lane);
+        {
+            if (lane < 32) s.dh.dist_lens[lane] = 0;
+            __syncwarp();
+            const uint32_t kd = warp_sort_small(lane < (unsigned)NDIST ? s.freq[288 + lane] : 0u, s.hw, lane);
+            warp_tree_lengths(s.hw, kd, 15, s.dh.dist_lens, s.bl32, &s.kraft, lane);
         }
-        __syncwarp();
-        {   // leaf depths by walking parents
-            const uint32_t root = 2 * k_used - 2;
-            for (uint32_t i = lane; i < k_used; i += 32) {
-                uint32_t node = i, dpt = 0;
-                while (node != root) {
-                    node = s.hw.parent[node];
-                    dpt++;
-                }
-                if (dpt > 15) dpt = 15;
-                atomicAdd(&s.bl32[dpt], 1u);
-                atomicAdd(&s.kraft, 1ull << (15 - dpt));
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            for (int b = 0; b < 16; b++) s.hw.bl_count[b] = (uint16_t)s.bl32[b];
-            huff_fix_overflow(s.hw.bl_count, 15, s.kraft);
-        }
-        __syncwarp();
-        for (uint32_t i = lane; i < k_used; i += 32) {  // rarest leaves take the longest codes
-            uint32_t cum = 0, L = 1;
-            for (int bits = 15; bits >= 1; bits--) {
-                cum += s.hw.bl_count[bits];
-                if (i < cum) {
-                    L = (uint32_t)bits;
-                    break;
-                }
-            }
-            s.dh.lit_lens[s.hw.order[i]] = (uint8_t)L;
-        }
-        __syncwarp();
         // canonical codes + block cost, both trees: per-length counts -> first code of every length (lane 0),
         // then the symbols in order, 32 at a time: code = first[len] + symbols of that length seen so far
         {
             uint32_t* cnt = s.bl32;          // [16] per-length counts, then first codes
-            uint32_t* seen = s.hw2.w;        // [16] running counts (the distance-tree scratch is free again)
+            uint32_t* seen = s.small;        // [16] running counts
             const uint32_t lt = (1u << lane) - 1;
             uint32_t cd = 0, cf = 0;
 #pragma unroll 1
@@ -886,28 +1025,93 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
             if (cf) atomicAdd(&s.cost_fix, cf);
         }
         __syncwarp();
-        if (lane == 0) plan_header_from_lengths(s.dh, s.hw);  // RLE + code-length code (serial, small)
+        // ---- dynamic header plan: trimmed alphabets, run-length coded lengths, the code-length code -------------
+        uint32_t nlit, ndist, n_rle, ncl, dyn_hdr_bits;
+        {
+            uint32_t last = 0;
+            for (uint32_t sy = lane; sy < (uint32_t)NLIT; sy += 32)
+                if (s.dh.lit_lens[sy]) last = sy + 1;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            nlit = last > 257 ? last : 257;
+            const uint32_t dm = __ballot_sync(0xffffffffu, lane < (unsigned)NDIST && s.dh.dist_lens[lane] != 0);
+            ndist = dm ? 32 - (uint32_t)__clz((int)dm) : 1;
+            uint16_t* ts = s.hw.parent;
+            uint16_t* te = s.hw.parent + 288;
+            n_rle = warp_rle(s.dh.lit_lens, nlit, s.dh.rle, 0, ts, te, lane);
+            n_rle += warp_rle(s.dh.dist_lens, ndist, s.dh.rle, n_rle, ts, te, lane);
+            // code-length code: frequencies, lengths (limit 7), canonical codes - 19 symbols, one per lane
+            s.small[lane] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < n_rle; i += 32) atomicAdd(&s.small[s.dh.rle[i] & 0xff], 1u);
+            __syncwarp();
+            if (lane < (unsigned)NCL) s.dh.cl_lens[lane] = 0;
+            const uint32_t kc = warp_sort_small(lane < (unsigned)NCL ? s.small[lane] : 0u, s.hw, lane);
+            warp_tree_lengths(s.hw, kc, 7, s.dh.cl_lens, s.bl32, &s.kraft, lane);
+            const uint32_t L = lane < (unsigned)NCL ? s.dh.cl_lens[lane] : 0u;
+            uint32_t code = 0, prev = 0, first = 0;
+#pragma unroll
+            for (int b = 1; b <= 7; b++) {
+                code = (code + prev) << 1;
+                prev = __popc(__ballot_sync(0xffffffffu, L == (uint32_t)b));
+                if (L == (uint32_t)b) first = code;
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, L ? L : 100u + lane);
+            const uint32_t clcode = L ? (L << 16) | bitrev(first + __popc(peers & ((1u << lane) - 1)), (int)L) : 0u;
+            if (lane < (unsigned)NCL) s.dh.cl_codes[lane] = clcode;
+            const uint32_t nz = __ballot_sync(0xffffffffu, lane < (unsigned)NCL && s.dh.cl_lens[cl_order((int)lane)] != 0);
+            ncl = nz ? 32 - (uint32_t)__clz((int)nz) : 0;
+            if (ncl < 4) ncl = 4;
+            __syncwarp();
+            uint32_t hb = 0;
+            for (uint32_t i = lane; i < n_rle; i += 32) {
+                const uint32_t sy = s.dh.rle[i] & 0xff;
+                hb += s.dh.cl_lens[sy] + (sy == 16 ? 2u : sy == 17 ? 3u : sy == 18 ? 7u : 0u);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) hb += __shfl_xor_sync(0xffffffffu, hb, o);
+            dyn_hdr_bits = 3 + 5 + 5 + 4 + 3 * ncl + hb;
+        }
+        // ---- block type by exact cost (like zlib), header bits -----------------------------------------------------
+        const uint64_t dyn_bits = (uint64_t)dyn_hdr_bits + s.cost_dyn, fix_bits = 3ull + s.cost_fix;
+        uint32_t mode_sel = dyn_bits < fix_bits ? 2u : 1u;
+        const uint64_t best_bits = dyn_bits < fix_bits ? dyn_bits : fix_bits;
+        const bool multi = (rec.flags & REC_MULTI) != 0;   // stored is decided for the whole stream (encode_long_kernel)
+        if (!multi && (uint64_t)rec.n + 5 <= (best_bits + 7) / 8) mode_sel = 0;
+        const uint32_t bfinal = (!multi || (rec.flags & REC_LAST)) ? 1u : 0u;
+        uint32_t hbits = 0;
+        for (uint32_t i = lane; i < 160; i += 32) s.hdr[i] = 0;
+        __syncwarp();
+        if (mode_sel == 2) {
+            // entry 0: BFINAL, BTYPE = 2, HLIT, HDIST, HCLEN; entries 1..ncl: the code-length code lengths in their
+            // transmission order; then the run-length coded lengths with their extra bits
+            const uint32_t total = 1 + ncl + n_rle;
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t e = base + lane;
+                uint32_t val = 0, nb = 0;
+                if (e == 0) {
+                    val = bfinal | (2u << 1) | ((nlit - 257) << 3) | ((ndist - 1) << 8) | ((ncl - 4) << 13);
+                    nb = 17;
+                } else if (e <= ncl) {
+                    val = s.dh.cl_lens[cl_order((int)(e - 1))];
+                    nb = 3;
+                } else if (e < total) {
+                    const uint32_t r = s.dh.rle[e - 1 - ncl], sy = r & 0xff, c = s.dh.cl_codes[sy];
+                    const uint32_t cl = c >> 16;
+                    val = (c & 0xffffu) | ((r >> 8) << cl);
+                    nb = cl + (sy == 16 ? 2u : sy == 17 ? 3u : sy == 18 ? 7u : 0u);
+                }
+                warp_put_bits(s.hdr, hbits, val, nb, lane);
+            }
+        } else if (mode_sel == 1) {
+            if (lane == 0) s.hdr[0] = bfinal | (1u << 1);
+            hbits = 3;
+        }
         __syncwarp();
         if (lane == 0) {
-            const uint64_t dyn_bits = (uint64_t)s.dh.bits + s.cost_dyn, fix_bits = 3ull + s.cost_fix;
-            uint32_t mode = dyn_bits < fix_bits ? 2u : 1u;
-            const uint64_t best_bits = dyn_bits < fix_bits ? dyn_bits : fix_bits;
-            const bool multi = (rec.flags & REC_MULTI) != 0;   // stored is decided for the whole stream (encode_long_kernel)
-            if (!multi && (uint64_t)rec.n + 5 <= (best_bits + 7) / 8) mode = 0;
-            const uint32_t bfinal = (!multi || (rec.flags & REC_LAST)) ? 1u : 0u;
-            BitWriter bw;
-            bw.buf = s.hdr;
-            bw.bitpos = 0;
-            if (mode == 2) {
-                write_dynamic_header(s.dh, bw, (int)bfinal);
-            } else if (mode == 1) {
-                bw.put(bfinal, 1);
-                bw.put(1, 2);
-            }
             s.bits = (uint32_t)best_bits;
-            bw.finish();
-            s.mode = mode;
-            s.hdr_bits = (uint32_t)bw.bitpos;
+            s.mode = mode_sel;
+            s.hdr_bits = hbits;
         }
         __syncwarp();
         const uint32_t mode = s.mode;
@@ -918,9 +1122,9 @@ __global__ void __launch_bounds__(HUFF_WARPS * 32) huffman_kernel(DeflArgs a) {
         }
         for (uint32_t i = lane; i < REC_WORDS; i += 32) g[i] = s.codes[i];
         if (mode != 0) {
-            const uint32_t hb = (s.hdr_bits + 7) >> 3;
-            uint8_t* gh = a.hdrs + (size_t)bj * 640;
-            for (uint32_t i = lane; i < hb; i += 32) gh[i] = s.hdr[i];
+            const uint32_t hw32 = (s.hdr_bits + 31) >> 5;
+            uint32_t* gh = reinterpret_cast<uint32_t*>(a.hdrs + (size_t)bj * 640);
+            for (uint32_t i = lane; i < hw32; i += 32) gh[i] = s.hdr[i];
         }
         if (lane == 0) {
             a.recs[bj].mode = mode;
