@@ -38,14 +38,18 @@ constexpr int DICT_CAP = 4;       // nearest dictionary candidates examined per 
 constexpr int DICT_HASH_BITS = 15; // the dictionary index lives in global memory: finer buckets, fewer false candidates
 constexpr uint32_t DICT_BUCKETS = 1u << DICT_HASH_BITS;
 constexpr uint32_t DICT_MAX = 32768;
-constexpr uint32_t NMAX_SMALL = 12288, NMAX_LARGE = 32768;
+// Size classes of parse_kernel (bytes per chunk): the small class keeps its match words in shared memory, the medium
+// and large ones in global scratch; small and medium fit two CTAs per SM, large one.  On the 8 KiB-average corpus
+// 83 % of the bytes are small, 17 % medium (12-20 KiB), < 0.5 % large.
+constexpr uint32_t NMAX_SMALL = 12288, NMAX_MEDIUM = 20480, NMAX_LARGE = 32768;
+constexpr int N_CLASS = 3, LONG_CLASS = 3;   // class 3: longer than NMAX_LARGE (multi-block streams)
 static_assert(NMAX_LARGE / 512 <= 64, "P3b keeps one moved-bit per element of a thread");
 constexpr int T_PARSE = 512;
 constexpr int TILE_SHIFT = 9;       // log2(T_PARSE): a scatter tile is T_PARSE consecutive positions
 static_assert((1 << TILE_SHIFT) == T_PARSE, "TILE_SHIFT");
 constexpr int T_ENCODE = 256;
 constexpr int HUFF_WARPS = 8;
-constexpr uint32_t BATCH_SMALL = 32768, BATCH_LARGE = 8192;  // chunks per batch (bounds the token scratch)
+constexpr uint32_t BATCH_SMALL = 32768, BATCH_MEDIUM = 16384, BATCH_LARGE = 8192;  // chunks per batch (bounds the token scratch)
 // Chunks longer than NMAX_LARGE become one zlib stream of several DEFLATE blocks of LONG_BLOCK input bytes.
 // Block b >= 1 is parsed like any chunk, with the PREVIOUS block of the same chunk in the role of the preset
 // dictionary (indexed on the device), which gives every position zlib's full 32 KiB window.
@@ -1380,7 +1384,7 @@ __global__ void classify_kernel(uint64_t start0, const uint64_t* __restrict__ cu
     const uint64_t len = cuts[j] - s;
     const uint64_t bound = len + 5 * (len / 65535 + 1) + 6 + 4 + 2 + 16;
     slot_size[k] = (bound + 15) & ~15ull;
-    const int c = len <= NMAX_SMALL ? 0 : (len <= NMAX_LARGE ? 1 : 2);
+    const int c = len <= NMAX_SMALL ? 0 : (len <= NMAX_MEDIUM ? 1 : (len <= NMAX_LARGE ? 2 : LONG_CLASS));
     const uint32_t pos = atomicAdd(&list_n[c], 1u);
     lists[(uint64_t)c * m + pos] = (uint32_t)k;
 }
@@ -1671,15 +1675,15 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         int rc = ensure_dict(ctx, d_zdict, dict_len, &dict_adler, st);
         if (rc) return rc;
     }
-    // misc: [slot_size m][slot_off m][sizes m+1][lists 3m u32][list_n 4 u32][totals][counters]
+    // misc: [slot_size m][slot_off m][sizes m+1][lists 4m u32][list_n 4 u32][totals][counters]
     const size_t n_counters = m + 8;   // one work counter per batch; a long chunk may be a batch of its own
-    const size_t misc_bytes = (3 * m + 2) * 8 + 3 * m * 4 + 64 + n_counters * 4 + 64;
+    const size_t misc_bytes = (3 * m + 2) * 8 + 4 * m * 4 + 64 + n_counters * 4 + 64;
     HMSE_SCRATCH(ctx, misc, uint8_t*, SLOT_DEFLATE_MISC, misc_bytes);
     uint64_t* slot_size = (uint64_t*)misc;
     uint64_t* slot_off = slot_size + m;
     uint64_t* sizes = slot_off + m;  // m + 1
     uint32_t* lists = (uint32_t*)(sizes + m + 1);
-    uint32_t* list_n = lists + 3 * m;
+    uint32_t* list_n = lists + 4 * m;
     uint64_t* d_tot = (uint64_t*)(((uintptr_t)(list_n + 4) + 7) & ~(uintptr_t)7);  // [stage total, out total]
     unsigned int* counters = (unsigned int*)(d_tot + 2);
     HMSE_CUDA(ctx, cudaMemsetAsync(list_n, 0, 48 + n_counters * 4, st));
@@ -1694,7 +1698,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t stage_bytes = mail[0];
     const uint32_t* hn = (const uint32_t*)(mail + 1);
-    const uint32_t n_class[3] = {hn[0], hn[1], hn[2]};
+    const uint32_t n_class[4] = {hn[0], hn[1], hn[2], hn[3]};
     HMSE_SCRATCH(ctx, stage, uint8_t*, SLOT_DEFLATE_STAGE, stage_bytes + 64);
 
     DeflArgs a;
@@ -1711,17 +1715,17 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     a.slot_off = slot_off;
     a.sizes = sizes;
 
-    const size_t sm_parse[2] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_LARGE, false)};
+    const size_t sm_parse[N_CLASS] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_MEDIUM, false), parse_smem(NMAX_LARGE, false)};
     const size_t sm_huff = sizeof(HuffSm) * HUFF_WARPS;
     HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<RS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[0]));
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[1]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[2]));
     HMSE_CUDA(ctx, cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_huff));
-    const uint32_t nmax_c[2] = {NMAX_SMALL, NMAX_LARGE};
-    const uint32_t batch_c[2] = {BATCH_SMALL, BATCH_LARGE};
-    const uint32_t ctas_c[2] = {(uint32_t)ctx->sm_count * 2, (uint32_t)ctx->sm_count};
+    const uint32_t nmax_c[N_CLASS] = {NMAX_SMALL, NMAX_MEDIUM, NMAX_LARGE};
+    const uint32_t batch_c[N_CLASS] = {BATCH_SMALL, BATCH_MEDIUM, BATCH_LARGE};
+    const uint32_t ctas_c[N_CLASS] = {(uint32_t)ctx->sm_count * 2, (uint32_t)ctx->sm_count * 2, (uint32_t)ctx->sm_count};
 
     // ---- plan of the long chunks (> NMAX_LARGE bytes): blocks of LONG_BLOCK bytes, batches aligned to chunks ----
-    const uint32_t n_long = n_class[2];
+    const uint32_t n_long = n_class[LONG_CLASS];
     std::vector<uint32_t> job_k, job_blk, ch_first, ch_nblk, batch_c0, batch_j0;   // batches: chunk / job boundaries
     std::vector<uint8_t> ch_stored;
     uint32_t long_jobs_max = 0, n_long_coded = 0;
@@ -1731,7 +1735,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         std::vector<uint64_t> lens(n_long);
         HMSE_SCRATCH(ctx, lens_dev, uint64_t*, SLOT_DEFLATE_LONG, (size_t)n_long * 8);
         KL(ctx);
-        long_len_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(start0, d_cuts, d_select, lists + 2 * m, n_long, lens_dev);
+        long_len_kernel<<<(n_long + 255) / 256, 256, 0, st>>>(start0, d_cuts, d_select, lists + (size_t)LONG_CLASS * m, n_long, lens_dev);
         HMSE_LAUNCH_CHECK(ctx);
         HMSE_CUDA(ctx, cudaMemcpyAsync(lens.data(), lens_dev, (size_t)n_long * 8, cudaMemcpyDeviceToHost, st));
         HMSE_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1781,7 +1785,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_jk, job_k.data(), nj * 4, cudaMemcpyHostToDevice, st));
             HMSE_CUDA(ctx, cudaMemcpyAsync(ldev + off_jb, job_blk.data(), nj * 4, cudaMemcpyHostToDevice, st));
             KL(ctx);
-            long_job_slot_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>((uint32_t*)(ldev + off_jk), (uint32_t)nj, lists + 2 * m);
+            long_job_slot_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, st>>>((uint32_t*)(ldev + off_jk), (uint32_t)nj, lists + (size_t)LONG_CLASS * m);
             HMSE_LAUNCH_CHECK(ctx);
         }
         HMSE_CUDA(ctx, cudaStreamSynchronize(st));   // the host vectors are pageable
@@ -1789,7 +1793,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
 
     // work scratch: tokens (u16 per input byte, per batch job), hist/codes, headers, records, large-class match
     size_t tok_bytes = 0, rec_jobs = 1;
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < N_CLASS; c++) {
         const uint32_t jobs = n_class[c] < batch_c[c] ? n_class[c] : batch_c[c];
         if ((size_t)jobs * nmax_c[c] * 2 > tok_bytes) tok_bytes = (size_t)jobs * nmax_c[c] * 2;
         if (jobs > rec_jobs) rec_jobs = jobs;
@@ -1797,9 +1801,14 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     if ((size_t)long_jobs_max * NMAX_LARGE * 2 > tok_bytes) tok_bytes = (size_t)long_jobs_max * NMAX_LARGE * 2;
     if (long_jobs_max > rec_jobs) rec_jobs = long_jobs_max;
     tok_bytes = (tok_bytes + 255) & ~(size_t)255;
-    uint32_t g_large = n_class[1] < ctas_c[1] ? n_class[1] : ctas_c[1];
+    // CTAs that keep their match words in global scratch (one slot of NMAX_LARGE words each, whatever the class)
+    uint32_t g_large = 0;
+    for (int c = 1; c < N_CLASS; c++) {
+        const uint32_t g = n_class[c] < ctas_c[c] ? n_class[c] : ctas_c[c];
+        if (g > g_large) g_large = g;
+    }
     if (long_jobs_max) {
-        const uint32_t g = long_jobs_max < ctas_c[1] ? long_jobs_max : ctas_c[1];
+        const uint32_t g = long_jobs_max < ctas_c[2] ? long_jobs_max : ctas_c[2];
         if (g > g_large) g_large = g;
     }
     const size_t work_bytes = tok_bytes + rec_jobs * (REC_WORDS * 4 + 640 + sizeof(ChunkRec)) +
@@ -1832,7 +1841,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     HT_BEGIN(ctx, HT_DEFLATE, st);
     uint32_t ci = 0;
     const uint32_t hmax = (uint32_t)ctx->sm_count * 3, emax = (uint32_t)ctx->sm_count * 8;
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < N_CLASS; c++) {
         a.list = lists + (size_t)c * m;
         a.nmax = nmax_c[c];
         a.match_smem = c == 0;
@@ -1859,7 +1868,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     if (n_long) {
         // coded long chunks, batch by batch: previous-block indexes, parse, Huffman, bit-level concatenation
         LongArgs la;
-        la.chunk_k = lists + 2 * m;
+        la.chunk_k = lists + (size_t)LONG_CLASS * m;
         la.chunk_first = (const uint32_t*)(ldev + off_first);
         la.chunk_nblk = (const uint32_t*)(ldev + off_nblk);
         la.stored_flag = ldev + off_flag;
@@ -1878,7 +1887,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             long_dict_kernel<<<jobs < (uint32_t)ctx->sm_count ? jobs : (uint32_t)ctx->sm_count, 1024, 0, st>>>(a);
             KL(ctx);
             PARSE_EV(0);
-            parse_kernel<5><<<jobs < ctas_c[1] ? jobs : ctas_c[1], T_PARSE, sm_parse[1], st>>>(a);
+            parse_kernel<5><<<jobs < ctas_c[2] ? jobs : ctas_c[2], T_PARSE, sm_parse[2], st>>>(a);
             PARSE_EV(1);
             const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
             KL(ctx);
@@ -1891,7 +1900,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             HMSE_LAUNCH_CHECK(ctx);
         }
         // whatever stays (level 0, oversize, or not compressible): stored blocks
-        a.list = lists + 2 * m;
+        a.list = lists + (size_t)LONG_CLASS * m;
         a.blk = nullptr;
         a.long_dicts = nullptr;
         a.stored_flag = ldev + off_flag;
