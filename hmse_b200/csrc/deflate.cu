@@ -375,44 +375,72 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             PROF(3)
             // Buckets are already ordered except for same-hash positions that were scattered in the same
             // tile (common in text: a word repeated within 512 bytes).  Such a group is contiguous in the
-            // bucket.  Most elements see at once that neither neighbour comes from their tile; the members
-            // of a group find their rank inside it (groups are tiny; a neighbour belongs to the same
-            // bucket iff its four bytes hash alike) and are rewritten through a temporary copy.
+            // bucket.  Pass 1 (all elements, cheap): an element whose neighbours both come from other tiles is in
+            // place; the others are compacted into a list.  Pass 2 (dense over the list): a listed element finds
+            // its rank inside its group (a neighbour belongs to the same bucket iff its stored hash agrees; groups
+            // are tiny) and writes itself to a temporary copy.  Pass 3 copies the moved elements back.
             uint16_t* s_tmp16 = reinterpret_cast<uint16_t*>(mptr);   // match words are not written before P4
-            uint64_t moved = 0;   // bit k: this thread's k-th element (index t + k*T) moved; nmax / T <= 64
+            uint16_t* s_list = s_E;                                    // the cursors are dead; bit 15 = "moved"
+            constexpr uint32_t LIST_CAP = CNT_WORDS * 2;
+            uint64_t moved = 0;   // elements handled in line because the list was full: bit k = index t' + k*T moved
+            auto fix_member = [&](uint32_t i) -> bool {
+                const uint32_t p = s_sorted[i];
+                const uint32_t tile = p >> TILE_SHIFT;
+                const uint32_t h = s_h16[p];
+                uint32_t first = i, smaller = 0, others = 0;
+                for (uint32_t j = i; j > 0;) {   // left neighbours of the same tile and bucket
+                    j--;
+                    const uint32_t q = s_sorted[j];
+                    if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
+                    first = j;
+                    smaller += q < p;
+                    others++;
+                }
+                for (uint32_t j = i + 1; j < nh; j++) {
+                    const uint32_t q = s_sorted[j];
+                    if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
+                    smaller += q < p;
+                    others++;
+                }
+                if (others) s_tmp16[first + smaller] = (uint16_t)p;
+                return others != 0;
+            };
+            if (t == 0) sm->n_big = 0;   // list length
+            __syncthreads();
             {
                 uint32_t k = 0;
-                for (uint32_t i = t; i < nh; i += T, k++) {
-                    const uint32_t p = s_sorted[i];
-                    const uint32_t tile = p >> TILE_SHIFT;
-                    const uint32_t ql = i ? s_sorted[i - 1] : 0xffffffffu, qr = i + 1 < nh ? s_sorted[i + 1] : 0xffffffffu;
-                    if ((ql >> TILE_SHIFT) != tile && (qr >> TILE_SHIFT) != tile) continue;
-                    const uint32_t h = s_h16[p];
-                    uint32_t first = i, smaller = 0, others = 0;
-                    for (uint32_t j = i; j > 0;) {   // left neighbours of the same tile and bucket
-                        j--;
-                        const uint32_t q = s_sorted[j];
-                        if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
-                        first = j;
-                        smaller += q < p;
-                        others++;
+                for (uint32_t ib = warp * 32; ib < nh; ib += T, k++) {   // warp-uniform trip count
+                    const uint32_t i = ib + lane;
+                    bool cand = false;
+                    if (i < nh) {
+                        const uint32_t tile = (uint32_t)s_sorted[i] >> TILE_SHIFT;
+                        const uint32_t ql = i ? s_sorted[i - 1] : 0xffffffffu, qr = i + 1 < nh ? s_sorted[i + 1] : 0xffffffffu;
+                        cand = (ql >> TILE_SHIFT) == tile || (qr >> TILE_SHIFT) == tile;
                     }
-                    for (uint32_t j = i + 1; j < nh; j++) {
-                        const uint32_t q = s_sorted[j];
-                        if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
-                        smaller += q < p;
-                        others++;
-                    }
-                    if (others) {
-                        s_tmp16[first + smaller] = (uint16_t)p;
-                        moved |= 1ull << k;
+                    const uint32_t b = __ballot_sync(0xffffffffu, cand);
+                    if (b) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&sm->n_big, (uint32_t)__popc(b));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (cand) {
+                            const uint32_t slot = base + __popc(b & ((1u << lane) - 1));
+                            if (slot < LIST_CAP) s_list[slot] = (uint16_t)i;
+                            else if (fix_member(i)) moved |= 1ull << k;   // (only on highly repetitive chunks)
+                        }
                     }
                 }
             }
             __syncthreads();
-            // every member of a group wrote one slot of the group's range, so the range is fully defined
-            for (uint64_t m = moved; m; m &= m - 1) {
-                const uint32_t i = t + (uint32_t)(__ffsll((long long)m) - 1) * T;
+            const uint32_t n_list = sm->n_big < LIST_CAP ? sm->n_big : LIST_CAP;
+            for (uint32_t j = t; j < n_list; j += T)
+                if (fix_member(s_list[j])) s_list[j] |= 0x8000u;
+            __syncthreads();
+            for (uint32_t j = t; j < n_list; j += T) {
+                const uint32_t e = s_list[j];
+                if (e & 0x8000u) s_sorted[e & 0x7fffu] = s_tmp16[e & 0x7fffu];
+            }
+            for (uint64_t mm = moved; mm; mm &= mm - 1) {
+                const uint32_t i = warp * 32 + lane + (uint32_t)(__ffsll((long long)mm) - 1) * T;
                 s_sorted[i] = s_tmp16[i];
             }
             __syncthreads();
