@@ -380,29 +380,17 @@ def run_ours(args):
                 d2h = r.d2h_bytes
         else:
             dbuf = ctx.empty(n_avail + 64, torch.uint8)[:n_avail]
-            cap_chunks = n_avail // cfg.min_size + 2
-            host_out = {"cuts": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
-                        "digests": torch.empty(cap_chunks * 32, dtype=torch.uint8, pin_memory=True),
-                        "canon": torch.empty(cap_chunks, dtype=torch.int64, pin_memory=True),
-                        "offsets": torch.empty(cap_chunks + 1, dtype=torch.int64, pin_memory=True),
-                        "blob": torch.empty(n_avail // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)}
-            api = ("hmse_b200.ShardedIngest.run on a device buffer filled from pinned host memory each step; cuts, digests, "
-                   "canon, offsets and the compressed blob copied back to pinned host memory each step")
+            host_out = pipe.host_buffers(n_avail)
+            api = ("hmse_b200.ShardedIngest.run(device buffer filled from pinned host memory each step, host=pinned result "
+                   "buffers): cuts, digests, canon, offsets and the compressed blob land in pinned host memory each step; the "
+                   "blob leaves in 8 pieces while the remaining chunks are compressed (global first-occurrence dedup needs "
+                   "every shard's digests before anything can be compressed, so the copy in is not overlapped)")
 
             def e2e_step():
                 nonlocal d2h
                 dbuf.copy_(host_in, non_blocking=True)
-                r = run(dbuf)
-                nb = r.blob.numel()
-                if nb > host_out["blob"].numel():
-                    host_out["blob"] = torch.empty(nb + (nb >> 3), dtype=torch.uint8, pin_memory=True)
-                host_out["cuts"][:r.n_chunks].copy_(r.cuts, non_blocking=True)
-                host_out["digests"][:r.n_chunks * 32].copy_(r.digests.view(-1), non_blocking=True)
-                host_out["canon"][:r.n_chunks].copy_(r.canon, non_blocking=True)
-                host_out["offsets"][:r.offsets.numel()].copy_(r.offsets, non_blocking=True)
-                host_out["blob"][:nb].copy_(r.blob, non_blocking=True)
-                d2h = r.n_chunks * (8 + 32 + 8) + r.offsets.numel() * 8 + nb
-                torch.cuda.synchronize()
+                r = pipe.run(dbuf, shard, eof, host=host_out)
+                d2h = r.d2h_bytes
 
         e2e_step()
         barrier()

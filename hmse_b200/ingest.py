@@ -352,8 +352,12 @@ class ShardedIngest(Ingest):
     def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, group=None):
         super().__init__(ctx, cdc, zdict, level)
         self.group = group
+        self._s_out = None
+        self._stage = [None, None]
 
-    def run(self, d: torch.Tensor, n_own: int, eof: bool, compress: bool = True) -> IngestResult:
+    def run(self, d: torch.Tensor, n_own: int, eof: bool, compress: bool = True, host=None, groups: int = 8):
+        """One shard.  With `host` (pinned buffers from host_buffers()) the results are left in host memory and the
+        compressed blob leaves the device in `groups` pieces while the rest is still being compressed."""
         import torch.distributed as dist
         ctx = self.ctx
         dev = ctx.tdev
@@ -384,11 +388,81 @@ class ShardedIngest(Ingest):
                                              first.data_ptr(), ctx.stream))
         canon, first = canon[:n], first[:n]
         sel = self.select_first(first)
+        if host is not None:
+            return self._compress_to_host(d, cuts, digests, canon, first, sel, entry, id_base, host, groups)
         if compress:
             blob, offs = ctx.compress(d, cuts, sel, self.zdict, self.level, start0=entry)
         else:
             blob, offs = ctx.empty(0, torch.uint8), ctx.empty(1, torch.int64).zero_()
         return IngestResult(cuts, digests, canon, first.view(torch.bool), sel, blob, offs, entry, id_base)
+
+    def host_buffers(self, n_avail: int):
+        """Pinned result buffers for `run(..., host=...)`, sized for a shard buffer of n_avail bytes."""
+        cap = n_avail // self.cdc.min_size + 2
+        return {"cuts": torch.empty(cap, dtype=torch.int64, pin_memory=True),
+                "digests": torch.empty(cap * 32, dtype=torch.uint8, pin_memory=True),
+                "canon": torch.empty(cap, dtype=torch.int64, pin_memory=True),
+                "offsets": torch.empty(cap + 1, dtype=torch.int64, pin_memory=True),
+                "blob": torch.empty(n_avail // 2 + (1 << 20), dtype=torch.uint8, pin_memory=True)}
+
+    def _compress_to_host(self, d, cuts, digests, canon, first, sel, entry, id_base, host, groups):
+        """The selected chunks are compressed in `groups` runs; the blob of run g travels to the host while run g+1
+        is compressed (two device buffers, a copy stream).  Streams and offsets equal one hmse_compress call."""
+        ctx = self.ctx
+        if self._s_out is None:
+            self._s_out = torch.cuda.Stream(ctx.tdev)
+        cur = torch.cuda.current_stream(ctx.device)
+        n, m = cuts.numel(), sel.numel()
+        ev0 = torch.cuda.Event()
+        ev0.record(cur)
+        self._s_out.wait_event(ev0)
+        with torch.cuda.stream(self._s_out):
+            host["cuts"][:n].copy_(cuts, non_blocking=True)
+            host["digests"][:n * 32].copy_(digests.view(-1), non_blocking=True)
+            host["canon"][:n].copy_(canon, non_blocking=True)
+        host["offsets"][0] = 0
+        d2h = n * 48
+        per = max(1, -(-m // max(1, groups)))
+        done = blob_total = 0
+        ev_out = [None, None]
+        keep = []
+        g = 0
+        while done < m:
+            part = sel[done:done + per]
+            j = g & 1
+            want = d.numel() // (2 * max(1, groups)) + (8 << 20)
+            if self._stage[j] is None or self._stage[j].numel() < want:
+                self._stage[j] = None
+                self._stage[j] = ctx.empty(want, torch.uint8)
+            if ev_out[j] is not None:
+                cur.wait_event(ev_out[j])
+            blob, offs = ctx.compress(d, cuts, part, self.zdict, self.level, start0=entry, out=self._stage[j])
+            if blob.data_ptr() != self._stage[j].data_ptr():
+                self._stage[j] = blob
+            mk, bk = part.numel(), blob.numel()
+            if blob_total + bk > host["blob"].numel():
+                raise ValueError("host blob buffer of %d bytes is too small" % host["blob"].numel())
+            offs_abs = offs[1:] + blob_total
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._s_out.wait_event(ev)
+            with torch.cuda.stream(self._s_out):
+                host["offsets"][1 + done:1 + done + mk].copy_(offs_abs, non_blocking=True)
+                host["blob"][blob_total:blob_total + bk].copy_(blob, non_blocking=True)
+                ev_out[j] = torch.cuda.Event()
+                ev_out[j].record(self._s_out)
+            keep.append(offs_abs)
+            d2h += mk * 8 + bk
+            done += mk
+            blob_total += bk
+            g += 1
+        cur.wait_stream(self._s_out)
+        cur.synchronize()
+        del keep
+        res = HostIngestResult(host["cuts"][:n], host["digests"][:n * 32].view(n, 32), host["canon"][:n],
+                               host["offsets"][:m + 1], host["blob"][:blob_total], h2d_bytes=0, d2h_bytes=d2h)
+        res.entry, res.id_base = entry, id_base
+        return res
 
 
 class ShardedSimilarity:

@@ -31,6 +31,11 @@ n_avail = (total - rank * per) if eof else per + cfg.max_size
 d = gen.generate(n_avail, byte_off=rank * per)
 zd = ctx.stage(pc.zdict())
 res = hmse_b200.ShardedIngest(ctx, cfg, zd).run(d, per, eof)
+pipe = hmse_b200.ShardedIngest(ctx, cfg, zd)
+hres = pipe.run(d, per, eof, host=pipe.host_buffers(n_avail), groups=3)
+assert np.array_equal(hres.cuts.numpy(), res.cuts.cpu().numpy()) and np.array_equal(hres.canon.numpy(), res.canon.cpu().numpy())
+assert np.array_equal(hres.digests.numpy(), res.digests.cpu().numpy())
+assert np.array_equal(hres.offsets.numpy(), res.offsets.cpu().numpy()) and np.array_equal(hres.blob.numpy(), res.blob.cpu().numpy())
 sig, keys, (lb, lk, li) = hmse_b200.ShardedSimilarity(ctx).run(d, res.cuts, start0=res.entry)
 torch.cuda.synchronize()
 out = dict(rank=rank, cuts=(res.cuts.cpu().numpy().view(np.uint64) + np.uint64(rank * per)).tolist(),
