@@ -64,6 +64,9 @@ SIGNATURES = {
     "hmse_minhash": (_I, [_P, _P, _U64, _P, _U64, _P, _U32, _P, _P]),
     "hmse_lsh_keys": (_I, [_P, _P, _U64, _U32, _U32, _P, _P]),
     "hmse_lsh_buckets": (_I, [_P, _P, _U64, _U32, _U64, _P, _P, _P, _P]),
+    "hmse_delta_bases": (_I, [_P, _P, _P, _P, _U64, _U32, _U64, _P, _U32, _P, _P]),
+    "hmse_delta_encode": (_I, [_P, _P, _U64, _P, _U64, _P, _P, _U64, _P, _PU64, _P]),
+    "hmse_delta_apply": (_I, [_P, _P, _P, _U64, _P, _P, _P, _P, _P, _P, _PU64, _P]),
     "hmse_corpus_lengths": (_I, [_P, C.POINTER(CorpusCfg), _P, _U64, _U64, _P, _P]),
     "hmse_corpus_render": (_I, [_P, C.POINTER(CorpusCfg), _P, _P, _U64, _U64, _P, _U64, _U64, _P, _P]),
 }

@@ -219,6 +219,45 @@ class Context:
                                              ids.data_ptr(), self.stream))
         return band, key, ids
 
+    def delta_bases(self, band: torch.Tensor, key: torch.Tensor, ids: torch.Tensor, n: int, bands: int,
+                    is_first: torch.Tensor, min_votes: int = 4, id_base: int = 0) -> torch.Tensor:
+        """base int64[n]: the root chunk each first-occurrence chunk would be delta-coded against, or -1."""
+        base = self.empty(n, torch.int64)
+        f = is_first.view(torch.uint8) if is_first.dtype == torch.bool else is_first
+        self.check(self.lib.hmse_delta_bases(self.h, band.data_ptr(), key.data_ptr(), ids.data_ptr(), n, bands, id_base,
+                                             f.contiguous().data_ptr(), min_votes, base.data_ptr(), self.stream))
+        return base
+
+    def delta_encode(self, d: torch.Tensor, cuts: torch.Tensor, base: torch.Tensor, start0: int = 0):
+        """(blob, offsets int64[n+1]); `base` is updated in place (-1 where the 20 % rule rejected the delta)."""
+        n = cuts.numel()
+        offsets = self.empty(n + 1, torch.int64)
+        total = C.c_uint64(0)
+        out_cap = 1 << 20
+        for _ in range(2):
+            out = self.empty(out_cap + _PAD, torch.uint8)
+            rc = self.lib.hmse_delta_encode(self.h, d.data_ptr(), start0, cuts.data_ptr(), n, base.data_ptr(),
+                                            out.data_ptr(), out_cap, offsets.data_ptr(), C.byref(total), self.stream)
+            if rc == _lib.HMSE_E_CAPACITY and total.value > out_cap:
+                out_cap = int(total.value)  # the encode is deterministic: the retry reproduces it
+                continue
+            self.check(rc)
+            return out[:total.value], offsets
+        raise HmseError(_lib.HMSE_E_CAPACITY, "hmse_delta_encode: capacity retry failed")
+
+    def delta_apply(self, blob: torch.Tensor, offsets: torch.Tensor, base_data: torch.Tensor, base_off: torch.Tensor,
+                    base_len: torch.Tensor, out_offsets: torch.Tensor):
+        """(out uint8, status int32[m], n_bad)."""
+        m = offsets.numel() - 1
+        total = int(out_offsets[-1]) if out_offsets.numel() else 0
+        out = self.empty(total + _PAD, torch.uint8)[:total]
+        status = self.empty(max(m, 1), torch.int32)[:m]
+        bad = C.c_uint64(0)
+        self.check(self.lib.hmse_delta_apply(self.h, blob.data_ptr(), offsets.data_ptr(), m, base_data.data_ptr(),
+                                             base_off.data_ptr(), base_len.data_ptr(), out.data_ptr(), out_offsets.data_ptr(),
+                                             status.data_ptr(), C.byref(bad), self.stream))
+        return out, status, int(bad.value)
+
 
 _contexts = {}
 
@@ -308,3 +347,38 @@ def similarity(data, cuts, cfg: SimConfig = SimConfig(), start0: int = 0, ctx: O
         return sig, keys, (band, key, ids)
     return (sig.cpu().numpy().view(np.uint32), _np_u64(keys),
             (band.cpu().numpy().view(np.uint32), _np_u64(key), _np_u64(ids)))
+
+
+def delta(data, cuts, keys, is_first, min_votes: int = 4, start0: int = 0, ctx: Optional[Context] = None):
+    """L4 delta coding (README.md:1328, 2160-2198): (base int64[n], blob uint8[...], offsets uint64[n+1]).
+    Chunk i is stored as a delta against chunk base[i] iff offsets[i+1] > offsets[i]; base[i] is -1 where no
+    delta is kept.  `keys` are the band keys of similarity() (uint64[n, bands], bands <= 32)."""
+    ctx = ctx or default_context()
+    dev = _is_dev(data)
+    d = ctx.stage(data)
+    c = ctx.stage_u64(cuts)
+    k = keys if _is_dev(keys) else torch.from_numpy(np.ascontiguousarray(keys, dtype=np.uint64).view(np.int64).copy()).to(ctx.tdev)
+    f = is_first if _is_dev(is_first) else torch.from_numpy(np.ascontiguousarray(is_first, dtype=np.uint8).copy()).to(ctx.tdev)
+    n, bands = k.shape
+    band, key, ids = ctx.lsh_buckets(k.contiguous())
+    base = ctx.delta_bases(band, key, ids, n, bands, f, min_votes)
+    blob, offs = ctx.delta_encode(d, c, base, start0)
+    return (base, blob, offs) if dev else (base.cpu().numpy(), blob.cpu().numpy(), _np_u64(offs))
+
+
+def delta_apply(blob, offsets, bases, base_sizes, sizes, ctx: Optional[Context] = None):
+    """The L4 read path: delta j applied to raw base j (the bases concatenated in `bases`, `base_sizes[j]` bytes
+    each) gives `sizes[j]` bytes; returns (raw uint8[sum(sizes)], status int32[m])."""
+    ctx = ctx or default_context()
+    dev = _is_dev(blob)
+    b = ctx.stage(blob)
+    offs = ctx.stage_u64(offsets)
+    bd = ctx.stage(bases)
+    to_np = lambda x: np.ascontiguousarray(x.cpu().numpy() if isinstance(x, torch.Tensor) else x)  # noqa: E731
+    bs = to_np(base_sizes).astype(np.uint64)
+    bo = np.concatenate([[np.uint64(0)], np.cumsum(bs, dtype=np.uint64)])[:-1]
+    sz = to_np(sizes).astype(np.uint64)
+    oo = np.concatenate([[np.uint64(0)], np.cumsum(sz, dtype=np.uint64)])
+    bl = torch.from_numpy(bs.astype(np.uint32).view(np.int32).copy()).to(ctx.tdev)
+    out, status, _ = ctx.delta_apply(b, offs, bd, ctx.stage_u64(bo), bl, ctx.stage_u64(oo))
+    return (out, status) if dev else (out.cpu().numpy(), status.cpu().numpy())

@@ -29,6 +29,10 @@ enum HmseSlot {
     SLOT_LSH_MISC,      // digit histograms
     SLOT_INFLATE_MISC,  // work counter, error count
     SLOT_ARCHIVE_MISC,  // slot map and reference counts of the index build
+    SLOT_DELTA_HEADS,   // bucket heads per (chunk, band) + root flags
+    SLOT_DELTA_MISC,    // slot offsets, delta sizes, candidate list
+    SLOT_DELTA_STAGE,   // per-candidate worst-case (len / 5) output slots
+    SLOT_DELTA_BAD,     // error count of the decoder
     SLOT_CORPUS,
     SLOT_COUNT
 };
@@ -36,7 +40,7 @@ enum HmseSlot {
 // Timed regions (hmse_timing_ms ids; also in include/hmse.h)
 constexpr int HMSE_PARSE_EVENTS = 128;
 enum HmseTimer {
-    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_INFLATE, HT_COUNT
+    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_INFLATE, HT_DELTA, HT_COUNT
 };
 
 struct hmse_ctx {

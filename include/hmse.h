@@ -70,6 +70,7 @@ uint64_t hmse_scratch_bytes(hmse_ctx* ctx);
 #define HMSE_T_MINHASH 6
 #define HMSE_T_LSH 7
 #define HMSE_T_INFLATE 8
+#define HMSE_T_DELTA 9
 int hmse_timing(hmse_ctx* ctx, int enable);
 int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms);
 /* Kernels launched through this ctx since hmse_create. */
@@ -206,6 +207,39 @@ int hmse_lsh_keys(hmse_ctx* ctx, const uint32_t* d_sig, uint64_t n, uint32_t ban
 /* All n*bands triples (band, key, id_base + j) sorted by (band, key, id). */
 int hmse_lsh_buckets(hmse_ctx* ctx, const uint64_t* d_keys, uint64_t n, uint32_t bands,
                      uint64_t id_base, uint32_t* d_band, uint64_t* d_key, uint64_t* d_id, void* stream);
+
+/* ---- L4 delta coding: replaces the "probe LSH index -> compute binary delta -> store if <= 20 %" step
+ *      (README.md:1328, 1555-1570) and the xdelta3 encode / patch calls of Appendix A (README.md:2160-2198).
+ *      The spec gives no byte format (xdelta3 / bsdiff are named, neither is vendored); the format is the COPY/ADD
+ *      op list of the spec's example (README.md:1402-1412) as oracle/deltacode.py defines it:
+ *        delta = op* ; op = varint(len << 1 | kind) ; kind 0 ADD: len literal bytes ; kind 1 COPY:
+ *        varint(zigzag(q - expect)), target += base[q : q + len], expect = q + len (0 at the start) ;
+ *        varint = unsigned LEB128.  Chunks and bases longer than 32768 bytes are never delta-coded. ------- */
+
+/* Base selection over the sorted triples of hmse_lsh_buckets (n chunks, bands <= 32, ids id_base..id_base+n-1):
+ * head(i, b) = first chunk of the bucket chunk i falls in for band b; votes(i, j) = bands whose head is j < i;
+ * root(i) = d_is_first[i] and no j reaches min_votes; d_base[i] = the root with the most votes >= min_votes
+ * (ties to the smaller index) as a LOCAL index, or -1 (also for duplicates).  Bases are roots: no chains. */
+int hmse_delta_bases(hmse_ctx* ctx, const uint32_t* d_band, const uint64_t* d_key, const uint64_t* d_id, uint64_t n,
+                     uint32_t bands, uint64_t id_base, const uint8_t* d_is_first, uint32_t min_votes, int64_t* d_base,
+                     void* stream);
+/* For every chunk i with d_base[i] >= 0: the delta of chunk i against chunk d_base[i] (greedy walk over 8-byte
+ * seeds of a 16384-bucket index of the base that keeps the smallest position per bucket; backward then forward
+ * extension), kept iff 5 * bytes <= chunk length; otherwise d_base[i] is reset to -1.  The kept deltas are packed
+ * in chunk order into d_out; d_offsets[n+1] bound them (empty for chunks without a delta); *total (host) =
+ * d_offsets[n].  On HMSE_E_CAPACITY *total holds the required out_cap (sum of len / 5 over the candidates always
+ * suffices).  d_data: 16-byte aligned, 16 readable bytes after the last chunk.  Synchronises `stream`. */
+int hmse_delta_encode(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts, uint64_t n,
+                      int64_t* d_base, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total,
+                      void* stream);
+/* Read path (README.md:2191-2198 "apply patch to decompressed base"): delta j = d_delta[d_delta_off[j] :
+ * d_delta_off[j+1]) applied to the raw base d_base[d_base_off[j] : + d_base_len[j]) yields
+ * d_out[d_out_off[j] : d_out_off[j+1]).  d_status[j] = 0, or 1 bad varint, 2 bad op length, 3 copy outside the
+ * base, 4 literals past the end of the delta, 5 trailing bytes; a bad delta never writes outside its range.
+ * *n_bad (may be null) = number of non-zero statuses (synchronises `stream`). */
+int hmse_delta_apply(hmse_ctx* ctx, const uint8_t* d_delta, const uint64_t* d_delta_off, uint64_t m,
+                     const uint8_t* d_base, const uint64_t* d_base_off, const uint32_t* d_base_len, uint8_t* d_out,
+                     const uint64_t* d_out_off, uint32_t* d_status, uint64_t* n_bad, void* stream);
 
 /* ---- Synthetic corpus (bench/test input, not part of the reference path): renders bytes
  *      [byte_off, byte_off + n) of the procedural wiki stream defined in oracle/corpus.py. ---- */

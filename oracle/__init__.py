@@ -18,6 +18,8 @@ with the contradictions resolved as SURVEY.md §0.2 records:
 * similarity() 128 x MurmurHash3_x86_32 over 4-byte shingles, running minimum
                from 0xFFFFFFFF (README.md:2578-2597), seeds 1..128
                (VALIDATION_METHODS.md:122), banding (README.md:2231-2235).
+* delta()      L4 delta coding against LSH-selected bases with the 20 % rule
+               (README.md:1328, 2160-2198); byte format defined in oracle/deltacode.py.
 
 Pinning status: the reference holds no golden vectors for any
 of these.  SHA-256, MurmurHash3 and zlib are pinned against their public
@@ -33,4 +35,5 @@ from .sha import digest, dedup  # noqa: F401
 from .deflate import compress, inflate_all, make_zdict  # noqa: F401
 from .minhash import (murmur3_32, minhash, minhash_c, band_keys, buckets,  # noqa: F401
                       similarity)
+from .deltacode import delta_bases, delta_encode, delta_apply, delta, lsh_heads  # noqa: F401
 from . import archive, corpus  # noqa: F401
