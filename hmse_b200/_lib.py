@@ -59,6 +59,7 @@ SIGNATURES = {
     "hmse_compress": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _U32, _I, _P, _U64, _P, _PU64, _P]),
     "hmse_debug_deflate_prof": (_I, [_PU64, _I]),
     "hmse_index_build": (_I, [_P, _P, _P, _U64, _P, _U64, _U64, _P, _U64, _P, _P, _P, _P]),
+    "hmse_index_build_l4": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _U64, _P, _P, _P, _P, _P, _P, _P, _U64, _PU64, _P]),
     "hmse_segment_copy": (_I, [_P, _P, _P, _P, _P, _U64, _P]),
     "hmse_inflate": (_I, [_P, _P, _P, _U64, _P, _U32, _P, _P, _P, _PU64, _P]),
     "hmse_minhash": (_I, [_P, _P, _U64, _P, _U64, _P, _U32, _P, _P]),

@@ -11,7 +11,7 @@ import torch
 
 from . import sharding
 from .api import Context
-from .config import CDCConfig
+from .config import CDCConfig, SimConfig
 
 
 @dataclass
@@ -25,6 +25,9 @@ class IngestResult:
     offsets: torch.Tensor     # int64 [m + 1]
     entry: int = 0            # offset of the first owned chunk (sharded)
     id_base: int = 0          # global id of local chunk 0 (sharded)
+    base: Optional[torch.Tensor] = None           # L4: int64 [n] base chunk of every chunk stored as a delta, else -1
+    delta_blob: Optional[torch.Tensor] = None     # L4: uint8 packed deltas (chunk order)
+    delta_offsets: Optional[torch.Tensor] = None  # L4: int64 [n + 1]
 
     @property
     def n_chunks(self) -> int:
@@ -44,17 +47,34 @@ class Ingest:
                                                       self.ctx.stream))
         return sel[:m.value]
 
-    def run(self, d: torch.Tensor, compress: bool = True) -> IngestResult:
+    def similarity_delta(self, d: torch.Tensor, cuts: torch.Tensor, first: torch.Tensor, sim: SimConfig, min_votes: int = 4):
+        """The L4 stage (README.md:1553-1570): MinHash -> band keys -> buckets -> base selection -> delta coding with
+        the 20 % rule.  Returns (base int64[n], delta blob, delta offsets int64[n+1])."""
+        ctx = self.ctx
+        keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim), sim)
+        band, key, ids = ctx.lsh_buckets(keys)
+        base = ctx.delta_bases(band, key, ids, cuts.numel(), sim.bands, first, min_votes)
+        dblob, doffs = ctx.delta_encode(d, cuts, base)
+        return base, dblob, doffs
+
+    def run(self, d: torch.Tensor, compress: bool = True, l4: Optional[SimConfig] = None, min_votes: int = 4) -> IngestResult:
+        """l4: also run the similarity layer; first occurrences that keep a delta are not compressed (`select` lists
+        the chunks of the chunk store only) and `base` / `delta_blob` / `delta_offsets` describe the deltas."""
         ctx = self.ctx
         cuts = ctx.chunk(d, self.cdc)
         digests = ctx.digest(d, cuts)
         canon, first = ctx.dedup(digests)
-        sel = self.select_first(first.view(torch.uint8))
+        base = dblob = doffs = None
+        stored = first
+        if l4 is not None and cuts.numel():
+            base, dblob, doffs = self.similarity_delta(d, cuts, first, l4, min_votes)
+            stored = first & (base < 0)
+        sel = self.select_first(stored.view(torch.uint8))
         if compress:
             blob, offs = ctx.compress(d, cuts, sel, self.zdict, self.level)
         else:
             blob, offs = ctx.empty(0, torch.uint8), ctx.empty(1, torch.int64).zero_()
-        return IngestResult(cuts, digests, canon, first, sel, blob, offs)
+        return IngestResult(cuts, digests, canon, first, sel, blob, offs, base=base, delta_blob=dblob, delta_offsets=doffs)
 
 
 @dataclass

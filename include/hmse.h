@@ -188,6 +188,19 @@ int hmse_inflate(hmse_ctx* ctx, const uint8_t* d_blob, const uint64_t* d_offsets
 int hmse_index_build(hmse_ctx* ctx, const uint8_t* d_digests, const int64_t* d_canon, uint64_t id_base,
                      const uint64_t* d_cuts, uint64_t start0, uint64_t n, const uint64_t* d_select, uint64_t m,
                      const uint64_t* d_offsets, uint8_t* d_index, uint8_t* d_pointers, void* stream);
+/* The same records when L4 stores some first-occurrence chunks as deltas (single GPU: canon and base are local
+ * indices).  d_select / d_offsets describe the m chunks in the chunk store (first occurrences that keep no delta);
+ * chunk c keeps a delta iff d_delta_off[c+1] > d_delta_off[c] (the outputs of hmse_delta_encode).  Writes the delta
+ * store: one `struct DeltaChunk` (README.md:2182-2189) per kept delta in chunk order, { u32 base = ChunkIndex entry
+ * number of the base chunk (the spec's "LBA lookup" goes through that entry), u16 base raw length - 1, u16 delta
+ * length, delta bytes }.  A pointer record whose position (lba * 512 + offset) is >= the chunk store size addresses
+ * the DeltaChunk at (position - store size) in the delta store.  Reference counts include one reference per delta on
+ * its base.  *delta_store_bytes (host) = bytes written; on HMSE_E_CAPACITY the required delta_store_cap. */
+int hmse_index_build_l4(hmse_ctx* ctx, const uint8_t* d_digests, const int64_t* d_canon, const uint64_t* d_cuts,
+                        uint64_t start0, uint64_t n, const uint64_t* d_select, uint64_t m, const uint64_t* d_offsets,
+                        const int64_t* d_base, const uint64_t* d_delta_off, const uint8_t* d_delta, uint8_t* d_index,
+                        uint8_t* d_pointers, uint8_t* d_delta_store, uint64_t delta_store_cap, uint64_t* delta_store_bytes,
+                        void* stream);
 /* d_dst[d_dst_off[i] : d_dst_off[i+1]) = d_src[d_src_off[i] : + the same length) for i < n (d_dst_off has n+1
  * entries, d_src_off n; d_src needs 4 readable bytes after its last segment). */
 int hmse_segment_copy(hmse_ctx* ctx, const uint8_t* d_src, const uint64_t* d_src_off, uint8_t* d_dst,

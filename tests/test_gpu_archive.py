@@ -74,3 +74,46 @@ def test_damaged_archives_are_rejected(ctx, corpus8):
         archive.Archive.frombytes(bytes(buf[:-1]))
     with pytest.raises(ValueError):
         archive.Archive.frombytes(b"XXXXXXXX" + bytes(buf[8:]))
+
+
+def test_l4_archive_records_equal_oracle_and_roundtrip(ctx, corpus8):
+    """Ingest with the similarity layer: near-duplicate first occurrences become DeltaChunk records
+    (README.md:2182-2189); records equal the oracle's byte for byte; both read paths rebuild the stream
+    (README.md:1329 "Read Base -> Retrieve Delta -> Apply Delta -> Decompress ... 100 % checksum pass")."""
+    import hmse_b200
+    from hmse_b200 import archive
+    zd = corpus.zdict()
+    data = np.concatenate([corpus8[:6 << 20], corpus8[2 << 20:3 << 20]])
+    r = hmse_b200.Ingest(ctx, hmse_b200.CDCConfig(), zd).run(ctx.stage(data), l4=hmse_b200.SimConfig())
+    base = r.base.cpu().numpy()
+    kept = base >= 0
+    assert kept.sum() > 20
+    first = r.is_first.cpu().numpy()
+    sel = r.select.cpu().numpy()
+    assert np.array_equal(sel, np.flatnonzero(first & ~kept))           # deltas are not compressed
+    cuts = r.cuts.cpu().numpy().view(np.uint64)
+    # the L4 outputs equal the oracle's on the same input
+    keys = oracle.band_keys(oracle.minhash_c(data, cuts))
+    wbase, wblob, woffs = oracle.delta(data, cuts, keys, first)
+    assert np.array_equal(base, wbase) and np.array_equal(r.delta_blob.cpu().numpy(), wblob)
+    assert np.array_equal(r.delta_offsets.cpu().numpy().view(np.uint64), woffs)
+    ar = archive.build(r, zd, ctx=ctx)
+    idx, ptr, dstore, nd = oracle.archive.records_l4(r.digests.cpu().numpy(), r.canon.cpu().numpy(), cuts, sel,
+                                                     r.offsets.cpu().numpy().view(np.uint64), base, wblob, woffs)
+    assert nd == kept.sum() == ar.n_delta
+    assert np.array_equal(ar.index, idx) and np.array_equal(ar.pointers, ptr) and np.array_equal(ar.delta_store, dstore)
+    buf = ar.tobytes()
+    assert buf == oracle.archive.pack(zd, idx, ptr, r.blob.cpu().numpy(), data.size, dstore, nd)
+    # smaller than the archive without L4
+    plain = archive.build(hmse_b200.Ingest(ctx, hmse_b200.CDCConfig(), zd).run(ctx.stage(data)), zd, ctx=ctx)
+    assert len(buf) < len(plain.tobytes())
+    back = archive.Archive.frombytes(buf)
+    assert back.n_delta == nd
+    assert archive.restore(back, ctx=ctx).tobytes() == data.tobytes()
+    assert oracle.archive.restore(buf) == data.tobytes()
+    # damage inside the delta store is caught (a COPY that runs outside its base, or a wrong length)
+    bad = bytearray(buf)
+    bad[len(buf) - ar.delta_store.size + 8] = 0xFF
+    bad[len(buf) - ar.delta_store.size + 9] = 0xFF
+    with pytest.raises(ValueError):
+        archive.restore(archive.Archive.frombytes(bytes(bad)), ctx=ctx)

@@ -168,3 +168,30 @@ def test_delta_pipeline_on_corpus(corpus8):
         assert D.delta_apply(blob[int(offs[i]):int(offs[i + 1])].tobytes(), raw[starts[j]:int(cuts[j])], len(t)) == t
         assert (int(offs[i + 1]) - int(offs[i])) * 5 <= len(t)
     assert np.all(np.diff(offs.astype(np.int64))[base < 0] == 0)
+
+
+def test_archive_v2_records_and_pure_python_restore(corpus8):
+    """Container v2 (DeltaChunk records, README.md:2182-2189) built and walked by the oracle alone."""
+    import struct
+    from oracle import archive as A
+    d = np.concatenate([corpus8[:3 << 20], corpus8[1 << 20:2 << 20]])
+    zd = oracle.corpus.zdict()
+    cuts = oracle.chunk_c(d)
+    dg = oracle.digest(d, cuts)
+    canon, first = oracle.dedup(dg)
+    keys = oracle.band_keys(oracle.minhash_c(d, cuts))
+    base, dblob, doffs = oracle.delta(d, cuts, keys, first)
+    sel = np.flatnonzero(first & (base < 0))
+    blob, offs = oracle.compress(d, cuts, sel, zd)
+    idx, ptr, dstore, nd = A.records_l4(dg, canon, cuts, sel, offs, base, dblob, doffs)
+    assert nd == (base >= 0).sum() > 5 and dstore.size == dblob.size + 8 * nd
+    # first DeltaChunk header: base slot, base raw length - 1, delta length
+    c0 = int(np.flatnonzero(base >= 0)[0])
+    bslot, blen, dl = struct.unpack_from("<IHH", dstore.tobytes(), 0)
+    starts = np.concatenate([[0], cuts[:-1]]).astype(np.int64)
+    assert sel[bslot] == base[c0] and blen + 1 == int(cuts[base[c0]]) - starts[base[c0]] and dl == int(doffs[c0 + 1] - doffs[c0])
+    buf = A.pack(zd, idx, ptr, blob, d.size, dstore, nd)
+    assert A.restore(buf) == d.tobytes()
+    # v1 is unchanged when nothing is delta coded
+    i1, p1 = A.records(dg, canon, cuts, np.flatnonzero(first), *oracle.compress(d, cuts, np.flatnonzero(first), zd)[1:])
+    assert A.restore(A.pack(zd, i1, p1, oracle.compress(d, cuts, np.flatnonzero(first), zd)[0], d.size)) == d.tobytes()
