@@ -63,6 +63,7 @@ SIGNATURES = {
     "hmse_segment_copy": (_I, [_P, _P, _P, _P, _P, _U64, _P]),
     "hmse_inflate": (_I, [_P, _P, _P, _U64, _P, _U32, _P, _P, _P, _PU64, _P]),
     "hmse_minhash": (_I, [_P, _P, _U64, _P, _U64, _P, _U32, _P, _P]),
+    "hmse_minhash_select": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _U32, _P, _P]),
     "hmse_lsh_keys": (_I, [_P, _P, _U64, _U32, _U32, _P, _P]),
     "hmse_lsh_buckets": (_I, [_P, _P, _U64, _U32, _U64, _P, _P, _P, _P]),
     "hmse_delta_bases": (_I, [_P, _P, _P, _P, _U64, _U32, _U64, _P, _U32, _P, _P]),

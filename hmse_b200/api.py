@@ -196,9 +196,17 @@ class Context:
         return out, status, int(bad.value)
 
     # -- L4 -------------------------------------------------------------------------------
-    def minhash(self, d: torch.Tensor, cuts: torch.Tensor, cfg: SimConfig, start0: int = 0) -> torch.Tensor:
-        m = cuts.numel()
+    def minhash(self, d: torch.Tensor, cuts: torch.Tensor, cfg: SimConfig, start0: int = 0,
+                select: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sig int32[m, n_perm] of every chunk, or (select: int64 chunk indices) of the selected chunks only."""
         seeds = torch.from_numpy(cfg.seed_array.view(np.int32).copy()).to(self.tdev)
+        if select is not None:
+            m = select.numel()
+            sig = self.empty(m * cfg.n_perm, torch.int32)
+            self.check(self.lib.hmse_minhash_select(self.h, d.data_ptr(), start0, cuts.data_ptr(), select.data_ptr(), m,
+                                                    seeds.data_ptr(), cfg.n_perm, sig.data_ptr(), self.stream))
+            return sig.view(m, cfg.n_perm)
+        m = cuts.numel()
         sig = self.empty(m * cfg.n_perm, torch.int32)
         self.check(self.lib.hmse_minhash(self.h, d.data_ptr(), start0, cuts.data_ptr(), m, seeds.data_ptr(), cfg.n_perm,
                                          sig.data_ptr(), self.stream))

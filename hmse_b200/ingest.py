@@ -51,9 +51,17 @@ class Ingest:
         """The L4 stage (README.md:1553-1570): MinHash -> band keys -> buckets -> base selection -> delta coding with
         the 20 % rule.  Returns (base int64[n], delta blob, delta offsets int64[n+1])."""
         ctx = self.ctx
-        keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim), sim)
+        # Only first occurrences are hashed (the spec computes MinHash after the exact-dedup miss, README.md:1553-1556).
+        # Duplicates never head a bucket (their first occurrence has the same keys and a smaller index), so selecting
+        # bases among the first occurrences alone, in their compacted index space, gives the same bases.
+        sel = self.select_first(first.view(torch.uint8))
+        m = sel.numel()
+        keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim, select=sel), sim)
         band, key, ids = ctx.lsh_buckets(keys)
-        base = ctx.delta_bases(band, key, ids, cuts.numel(), sim.bands, first, min_votes)
+        ones = torch.ones(m, dtype=torch.uint8, device=ctx.tdev)
+        base_u = ctx.delta_bases(band, key, ids, m, sim.bands, ones, min_votes)
+        base = torch.full((cuts.numel(),), -1, dtype=torch.int64, device=ctx.tdev)
+        base[sel] = torch.where(base_u >= 0, sel[base_u.clamp(min=0)], base_u)
         dblob, doffs = ctx.delta_encode(d, cuts, base)
         return base, dblob, doffs
 

@@ -214,6 +214,11 @@ int hmse_segment_copy(hmse_ctx* ctx, const uint8_t* d_src, const uint64_t* d_src
 int hmse_minhash(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
                  uint64_t n_chunks, const uint32_t* d_seeds, uint32_t n_perm, uint32_t* d_sig,
                  void* stream);
+/* The same for the m chunks d_select[0..m) only: d_sig[k][n_perm] = signature of chunk d_select[k] (the spec computes
+ * MinHash only for chunks that passed exact dedup, README.md:1553-1556). */
+int hmse_minhash_select(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
+                        const uint64_t* d_select, uint64_t m, const uint32_t* d_seeds, uint32_t n_perm, uint32_t* d_sig,
+                        void* stream);
 /* d_keys[j][bands] = FNV-1a-64 of the band's rows*4 little-endian signature bytes. */
 int hmse_lsh_keys(hmse_ctx* ctx, const uint32_t* d_sig, uint64_t n, uint32_t bands, uint32_t rows,
                   uint64_t* d_keys, void* stream);

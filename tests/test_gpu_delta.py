@@ -214,3 +214,22 @@ def test_roundtrip_larger_stream(ctx):
     assert bad == 0
     want = torch.cat([d[int(s):int(e)] for s, e in zip(starts[kept].tolist(), cuts[kept].tolist())])
     assert torch.equal(out, want)
+
+
+def test_minhash_select_rows_equal_full_rows(ctx, corpus8):
+    """hmse_minhash_select: signatures of the selected chunks only, equal to the oracle's rows; odd and even shingle
+    counts and tiny chunks exercise the pairwise inner loop."""
+    import torch
+    import hmse_b200
+    d = corpus8[:2 << 20]
+    cuts = oracle.chunk_c(d)
+    want = oracle.minhash_c(d, cuts)
+    sel = np.flatnonzero(np.arange(cuts.size) % 3 != 1)
+    dd = ctx.stage(d)
+    got = ctx.minhash(dd, _t64(cuts), hmse_b200.SimConfig(), select=torch.from_numpy(sel.astype(np.int64)).cuda())
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want[sel])
+    # chunk lengths 0..70 bytes: 0, 1, 2 ... shingles
+    small = np.cumsum(np.arange(1, 71)).astype(np.uint64)
+    sd = corpus8[:int(small[-1])]
+    got = ctx.minhash(ctx.stage(sd), _t64(small), hmse_b200.SimConfig())
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), oracle.minhash_c(sd, small))
