@@ -233,3 +233,34 @@ def test_minhash_select_rows_equal_full_rows(ctx, corpus8):
     sd = corpus8[:int(small[-1])]
     got = ctx.minhash(ctx.stage(sd), _t64(small), hmse_b200.SimConfig())
     assert np.array_equal(got.cpu().numpy().view(np.uint32), oracle.minhash_c(sd, small))
+
+
+def test_gpu_matches_committed_delta_golden(ctx):
+    """GPU vs tests/golden/delta_golden.json directly (not through the oracle)."""
+    import hashlib
+    import json
+    import os
+    import sys
+    import hmse_b200
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_delta_golden as mk
+    g = json.load(open(os.path.join(here, "golden", "delta_golden.json")))
+    pairs = mk.pairs()
+    blob, offs, got_base = _check_pairs(ctx, pairs)
+    for k, want in enumerate(g["pairs"]):
+        got = blob[int(offs[2 * k + 1]):int(offs[2 * k + 2])].tobytes()
+        assert (got.hex() if got else None) == want["delta_hex"], k
+    d = hmse_b200.corpus.DeviceCorpus(ctx).generate(g["n"])
+    assert hashlib.sha256(d.cpu().numpy().tobytes()).hexdigest() == g["input_sha256"]
+    r = hmse_b200.Ingest(ctx).run(d, compress=False, l4=hmse_b200.SimConfig())
+    base = r.base.cpu().numpy()
+    assert r.n_chunks == g["chunks"]
+    assert hashlib.sha256(base.astype("<i8").tobytes()).hexdigest() == g["base_sha256"]
+    assert [[int(i), int(base[i])] for i in np.flatnonzero(base >= 0)] == g["kept"]
+    dblob = r.delta_blob.cpu().numpy()
+    doffs = r.delta_offsets.cpu().numpy().view(np.uint64)
+    assert dblob.size == g["delta_bytes"] and hashlib.sha256(dblob.tobytes()).hexdigest() == g["blob_sha256"]
+    assert hashlib.sha256(doffs.astype("<u8").tobytes()).hexdigest() == g["offsets_sha256"]
+    for i, hx in zip(np.flatnonzero(base >= 0)[:3], g["first_deltas_hex"]):
+        assert dblob[int(doffs[i]):int(doffs[i + 1])].tobytes().hex() == hx

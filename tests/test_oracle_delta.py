@@ -195,3 +195,32 @@ def test_archive_v2_records_and_pure_python_restore(corpus8):
     # v1 is unchanged when nothing is delta coded
     i1, p1 = A.records(dg, canon, cuts, np.flatnonzero(first), *oracle.compress(d, cuts, np.flatnonzero(first), zd)[1:])
     assert A.restore(A.pack(zd, i1, p1, oracle.compress(d, cuts, np.flatnonzero(first), zd)[0], d.size)) == d.tobytes()
+
+
+def _delta_golden():
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_delta_golden
+    return json.load(open(os.path.join(here, "golden", "delta_golden.json"))), make_delta_golden
+
+
+def test_oracle_matches_committed_delta_golden():
+    import hashlib
+    g, mk = _delta_golden()
+    for (b, t), want in zip(mk.pairs(), g["pairs"]):
+        assert hashlib.sha256(b).hexdigest() == want["base_sha256"] and hashlib.sha256(t).hexdigest() == want["target_sha256"]
+        dl = D.delta_encode(t, b)
+        assert (None if dl is None else dl.hex()) == want["delta_hex"]
+        if dl is not None:
+            assert D.delta_apply(dl, b, len(t)) == t
+    d = oracle.corpus.generate(g["n"])
+    assert hashlib.sha256(d.tobytes()).hexdigest() == g["input_sha256"]
+    cuts = oracle.chunk_c(d)
+    _, first = oracle.dedup(oracle.digest(d, cuts))
+    base, blob, offs = oracle.delta(d, cuts, oracle.band_keys(oracle.minhash_c(d, cuts)), first)
+    assert [[int(i), int(base[i])] for i in np.flatnonzero(base >= 0)] == g["kept"]
+    assert hashlib.sha256(blob.tobytes()).hexdigest() == g["blob_sha256"] and blob.size == g["delta_bytes"]
+    assert hashlib.sha256(offs.astype("<u8").tobytes()).hexdigest() == g["offsets_sha256"]
