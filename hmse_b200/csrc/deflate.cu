@@ -345,17 +345,46 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 reinterpret_cast<uint2*>(s_h16)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
             }
             __syncthreads();
-            // ---- P2: exclusive scan: E[h+1] = start of bucket h (cursor), E[0] = 0 ------------------
-            const uint32_t per = NBUCKET / T;  // buckets per thread (T divides NBUCKET)
+            // ---- P2: exclusive scan: E[h+1] = start of bucket h (cursor), E[0] = 0.  E[0] holds no count, so this is
+            //      the exclusive scan of the u16 array E[0 .. NBUCKET] itself.  A warp owns 256 consecutive words (512
+            //      entries) and reads them row by row, lane = word: conflict-free, where a thread walking its own 16
+            //      consecutive entries put eight lanes on every bank (a fifth of the kernel's shared-memory wavefronts).
             {
-                uint32_t sum = 0;
-                for (uint32_t i = 0; i < per; i++) sum += s_E[t * per + i + 1];
-                uint32_t tot;
-                uint32_t run = block_excl_scan(sum, sm->warp_tmp, &tot);
-                for (uint32_t i = 0; i < per; i++) {
-                    const uint32_t c = s_E[t * per + i + 1];
-                    s_E[t * per + i + 1] = (uint16_t)run;
-                    run += c;
+                static_assert(NBUCKET / 2 == 256 * (T_PARSE / 32), "one 256-word span per warp");
+                uint32_t* wp = s_cnt32 + warp * 256 + lane;
+                uint32_t wv[8], pre[8], carry = 0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    wv[r] = wp[r * 32];
+                    const uint32_t sum2 = (wv[r] & 0xffffu) + (wv[r] >> 16);
+                    uint32_t inc = sum2;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (unsigned)o) inc += tt;
+                    }
+                    pre[r] = carry + inc - sum2;
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0) sm->warp_tmp[warp] = carry;
+                __syncthreads();
+                if (warp == 0) {
+                    const uint32_t v = lane < nwarps ? sm->warp_tmp[lane] : 0u;
+                    uint32_t inc = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (unsigned)o) inc += tt;
+                    }
+                    sm->warp_tmp[lane] = inc - v;
+                    if (lane == 31) s_E[NBUCKET] = (uint16_t)inc;   // the entry past the last full word: everything before it
+                }
+                __syncthreads();
+                const uint32_t base = sm->warp_tmp[warp];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const uint32_t e0 = base + pre[r];
+                    wp[r * 32] = e0 | ((e0 + (wv[r] & 0xffffu)) << 16);
                 }
             }
             __syncthreads();
@@ -471,8 +500,14 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     const int i = (int)(28 * w) - 4 + (int)lane;
                     if (w < nwin && i >= 0 && i < (int)nh) {
                         const uint32_t p = s_sorted[i];
-                        r.v = ld32u(s_data32, p);
-                        r.pp = p | ((p ? (uint32_t)s_data[p - 1] : CHUNK_PREV0) << 16);
+                        // bytes p-1 .. p+3 lie in two consecutive words: one pair of loads serves both the value and
+                        // the byte before it
+                        const uint32_t pm = p ? p - 1 : 0u;
+                        const uint32_t w0 = s_data32[pm >> 2], w1 = s_data32[(pm >> 2) + 1];
+                        const uint32_t sh8 = (pm & 3) * 8;
+                        const uint32_t lo5 = __funnelshift_r(w0, w1, sh8);          // bytes pm .. pm+3
+                        r.v = p ? __funnelshift_r(lo5, w1 >> sh8, 8) : lo5;        // bytes p .. p+3
+                        r.pp = p | ((p ? (lo5 & 0xffu) : CHUNK_PREV0) << 16);
                         if (use_dict && lane >= 4) r.bk = __ldg(&dict->bk4[hash_dict(r.v)]);
                     }
                     return r;
