@@ -381,7 +381,9 @@ class ShardedIngest(Ingest):
         super().__init__(ctx, cdc, zdict, level)
         self.group = group
         self._s_out = None
+        self._s_in = None
         self._stage = [None, None]
+        self._in = [None, None]
 
     def run(self, d: torch.Tensor, n_own: int, eof: bool, compress: bool = True, host=None, groups: int = 8):
         """One shard.  With `host` (pinned buffers from host_buffers()) the results are left in host memory and the
@@ -423,6 +425,51 @@ class ShardedIngest(Ingest):
         else:
             blob, offs = ctx.empty(0, torch.uint8), ctx.empty(1, torch.int64).zero_()
         return IngestResult(cuts, digests, canon, first.view(torch.bool), sel, blob, offs, entry, id_base)
+
+    def run_batches(self, batches, n_own: int, eof: bool, host, groups: int = 8):
+        """A sequence of shard buffers in pinned host memory (one per step of a continuous ingest): generator of
+        HostIngestResult, one per batch, each valid until the next is requested.  The device input is double
+        buffered - batch k+1 travels host->device on its own stream while batch k is chunked, deduplicated and
+        compressed and its blob travels back - so a step costs max(copy in, compute, copy out) instead of their sum
+        (global first-occurrence dedup needs every shard's digests before anything is compressed, so the copy in
+        cannot be hidden inside one batch).  Every rank must iterate in step."""
+        ctx = self.ctx
+        cur = torch.cuda.current_stream(ctx.device)
+        if self._s_in is None:
+            self._s_in = torch.cuda.Stream(ctx.tdev)
+        ready, free = [None, None], [None, None]
+
+        def fetch(slot: int, hb: torch.Tensor) -> int:
+            n = hb.numel()
+            if self._in[slot] is None or self._in[slot].numel() < n + 64:
+                self._in[slot] = None
+                self._in[slot] = ctx.empty(n + 64, torch.uint8)
+            if free[slot] is not None:
+                self._s_in.wait_event(free[slot])
+            with torch.cuda.stream(self._s_in):
+                self._in[slot][:n].copy_(hb.view(-1), non_blocking=True)
+                ready[slot] = torch.cuda.Event()
+                ready[slot].record(self._s_in)
+            return n
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        n_cur, k = fetch(0, nxt), 0
+        while True:
+            slot = k & 1
+            nxt = next(it, None)
+            n_next = fetch(slot ^ 1, nxt) if nxt is not None else 0
+            cur.wait_event(ready[slot])
+            res = self.run(self._in[slot][:n_cur], n_own, eof, host=host, groups=groups)
+            free[slot] = torch.cuda.Event()
+            free[slot].record(cur)
+            res.h2d_bytes = n_cur
+            yield res
+            if nxt is None:
+                return
+            n_cur, k = n_next, k + 1
 
     def host_buffers(self, n_avail: int):
         """Pinned result buffers for `run(..., host=...)`, sized for a shard buffer of n_avail bytes."""

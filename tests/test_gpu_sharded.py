@@ -36,6 +36,15 @@ hres = pipe.run(d, per, eof, host=pipe.host_buffers(n_avail), groups=3)
 assert np.array_equal(hres.cuts.numpy(), res.cuts.cpu().numpy()) and np.array_equal(hres.canon.numpy(), res.canon.cpu().numpy())
 assert np.array_equal(hres.digests.numpy(), res.digests.cpu().numpy())
 assert np.array_equal(hres.offsets.numpy(), res.offsets.cpu().numpy()) and np.array_equal(hres.blob.numpy(), res.blob.cpu().numpy())
+# double-buffered batches from pinned host memory: every batch equals the plain run
+hin = torch.empty(n_avail, dtype=torch.uint8, pin_memory=True); hin.copy_(d)
+nb = 0
+for hb in pipe.run_batches([hin, hin, hin], per, eof, host=pipe.host_buffers(n_avail), groups=2):
+    assert np.array_equal(hb.cuts.numpy(), res.cuts.cpu().numpy()) and np.array_equal(hb.canon.numpy(), res.canon.cpu().numpy())
+    assert np.array_equal(hb.offsets.numpy(), res.offsets.cpu().numpy()) and np.array_equal(hb.blob.numpy(), res.blob.cpu().numpy())
+    assert hb.h2d_bytes == n_avail
+    nb += 1
+assert nb == 3
 sig, keys, (lb, lk, li) = hmse_b200.ShardedSimilarity(ctx).run(d, res.cuts, start0=res.entry)
 torch.cuda.synchronize()
 out = dict(rank=rank, cuts=(res.cuts.cpu().numpy().view(np.uint64) + np.uint64(rank * per)).tolist(),
