@@ -264,3 +264,63 @@ def test_gpu_matches_committed_delta_golden(ctx):
     assert hashlib.sha256(doffs.astype("<u8").tobytes()).hexdigest() == g["offsets_sha256"]
     for i, hx in zip(np.flatnonzero(base >= 0)[:3], g["first_deltas_hex"]):
         assert dblob[int(doffs[i]):int(doffs[i + 1])].tobytes().hex() == hx
+
+
+def test_l4_pipeline_edge_cases(ctx, corpus8):
+    """Ingest.run(l4=...) on degenerate streams: empty, one chunk, every chunk a duplicate, chunks above the 32 KiB
+    delta limit (they are never delta coded), and an archive round trip of each."""
+    import torch
+    import hmse_b200
+    from hmse_b200 import archive
+    zd = oracle.corpus.zdict()
+    sim = hmse_b200.SimConfig()
+    ing = hmse_b200.Ingest(ctx, hmse_b200.CDCConfig(), zd)
+    # empty input
+    r = ing.run(ctx.stage(np.zeros(0, dtype=np.uint8)), l4=sim)
+    assert r.n_chunks == 0 and r.base is None
+    # one chunk
+    one = corpus8[:1500]
+    r = ing.run(ctx.stage(one), l4=sim)
+    assert r.n_chunks == 1 and r.base.cpu().tolist() == [-1] and r.delta_blob.numel() == 0
+    assert archive.restore(archive.build(r, zd, ctx=ctx), ctx=ctx).tobytes() == one.tobytes()
+    # every chunk after the first copy is an exact duplicate: nothing is similar-but-different
+    rep = np.concatenate([corpus8[:300000]] * 3)
+    r = ing.run(ctx.stage(rep), l4=sim)
+    base = r.base.cpu().numpy()
+    first = r.is_first.cpu().numpy()
+    assert (base[~first] == -1).all()
+    assert archive.restore(archive.build(r, zd, ctx=ctx), ctx=ctx).tobytes() == rep.tobytes()
+    # 64 KiB maximum chunk size: near-duplicate chunks longer than 32768 bytes keep no delta, shorter ones do
+    m32 = hmse_b200.CDCConfig.for_avg(32768)
+    big_cfg = hmse_b200.CDCConfig(8192, 32768, 65536, m32.mask_s, m32.mask_l)     # chunks of 8 .. 64 KiB
+    a = corpus8[:1 << 20]
+    b = a.copy()
+    b[5000::40000] ^= 0x20
+    both = np.concatenate([a, b])
+    r = hmse_b200.Ingest(ctx, big_cfg, zd).run(ctx.stage(both), l4=sim)
+    cuts = r.cuts.cpu().numpy().view(np.uint64)
+    ln = np.diff(np.concatenate([[0], cuts]).astype(np.int64))
+    base = r.base.cpu().numpy()
+    assert (ln > 32768).any() and (base >= 0).any()
+    assert (base[ln > 32768] == -1).all()
+    assert (ln[base[base >= 0]] <= 32768).all()
+    keys = oracle.band_keys(oracle.minhash_c(both, cuts))
+    wbase, wblob, _ = oracle.delta(both, cuts, keys, r.is_first.cpu().numpy())
+    assert np.array_equal(base, wbase) and np.array_equal(r.delta_blob.cpu().numpy(), wblob)
+    assert archive.restore(archive.build(r, zd, ctx=ctx), ctx=ctx).tobytes() == both.tobytes()
+
+
+def test_delta_api_errors(ctx):
+    import torch
+    import hmse_b200
+    n = 8
+    keys = torch.arange(n * 64, dtype=torch.int64).view(n, 64).cuda()
+    band, key, ids = ctx.lsh_buckets(keys)
+    ones = torch.ones(n, dtype=torch.uint8).cuda()
+    with pytest.raises(hmse_b200.HmseError):
+        ctx.delta_bases(band, key, ids, n, 64, ones, 4)          # more than 32 bands
+    k32 = torch.arange(n * 32, dtype=torch.int64).view(n, 32).cuda()
+    band, key, ids = ctx.lsh_buckets(k32)
+    with pytest.raises(hmse_b200.HmseError):
+        ctx.delta_bases(band, key, ids, n, 32, ones, 0)          # min_votes 0
+    assert ctx.delta_bases(band, key, ids, n, 32, ones, 4).cpu().tolist() == [-1] * n
