@@ -33,7 +33,13 @@ using namespace dfl;
 
 namespace {
 
-constexpr int OWN_CAP = 4;        // nearest own-chunk candidates examined per position
+constexpr int OWN_CAP = 4;        // nearest own-chunk candidates examined per position, at most (large class)
+// Own-chunk candidates per size class.  On the 8 KiB-average corpus most matches of a short chunk come from the preset
+// dictionary: with two own candidates instead of four the small class loses 0.06 % (4 KiB chunks) to 0.2 % (8 KiB CDC
+// chunks) of size and stays at zlib-6 parity (1.0001x), while a 32 KiB chunk would lose 1.8 % - so the depth follows
+// the class (CPU model, tests/model: own/dict 4/4, 3/4, 2/4 -> 0.9978 / 0.9985 / 1.0001 x zlib-6 on CDC chunks;
+// 0.9982 / 0.9994 / 1.0020 on 16 KiB; 1.0051 / 1.0115 / 1.0231 on 32 KiB).
+constexpr int OWN_SMALL = 2, OWN_MEDIUM = 3, OWN_LARGE = 4;
 constexpr int DICT_CAP = 4;       // nearest dictionary candidates examined per position (one 16-byte bucket record)
 constexpr int DICT_HASH_BITS = 15; // the dictionary index lives in global memory: finer buckets, fewer false candidates
 constexpr uint32_t DICT_BUCKETS = 1u << DICT_HASH_BITS;
@@ -242,8 +248,10 @@ __device__ __forceinline__ bool mw_is_match(uint32_t mw) { return (mw >> 16) != 
 // =================================================================================================
 // parse_kernel
 // =================================================================================================
-template <int RS>   // log2 of the range length of the chain passes P4c-P7
+template <int RS, int OWN>   // log2 of the range length of the chain passes P4c-P7; own-chunk candidates per position
 __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
+    static_assert(OWN >= 1 && OWN <= OWN_CAP, "own candidates");
+    constexpr int WIN = 32 - OWN;   // new sorted indices per window: the first OWN lanes only carry context
     constexpr uint32_t RL = 1u << RS;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t T = blockDim.x, t = threadIdx.x;
@@ -491,13 +499,13 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 const bool use_dict = dlen != 0;
                 uint32_t* plist = s_cnt32 + warp * PAIR_CAP;   // the bucket table is dead: E is not needed to walk s_sorted
                 uint32_t pcnt = 0;                             // warp-uniform
-                const uint32_t nwin = (nh + 27) / 28;
+                const uint32_t nwin = (nh + WIN - 1) / WIN;
                 struct StA { uint32_t pp, v; uint4 bk; };
                 // pp = position | previous byte << 16; lanes outside the index range carry pp = ~0
                 auto stageA = [&](uint32_t w) {
                     StA r;
                     r.pp = 0xffffffffu; r.v = 0; r.bk = make_uint4(0, 0, 0, 0);
-                    const int i = (int)(28 * w) - 4 + (int)lane;
+                    const int i = (int)(WIN * w) - OWN + (int)lane;
                     if (w < nwin && i >= 0 && i < (int)nh) {
                         const uint32_t p = s_sorted[i];
                         // bytes p-1 .. p+3 lie in two consecutive words: one pair of loads serves both the value and
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         const uint32_t lo5 = __funnelshift_r(w0, w1, sh8);          // bytes pm .. pm+3
                         r.v = p ? __funnelshift_r(lo5, w1 >> sh8, 8) : lo5;        // bytes p .. p+3
                         r.pp = p | ((p ? (lo5 & 0xffu) : CHUNK_PREV0) << 16);
-                        if (use_dict && lane >= 4) r.bk = __ldg(&dict->bk4[hash_dict(r.v)]);
+                        if (use_dict && lane >= OWN) r.bk = __ldg(&dict->bk4[hash_dict(r.v)]);
                     }
                     return r;
                 };
@@ -534,13 +542,13 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     s0 = s1;
                     s1 = stageA(w + 2 * nwarps);
 
-                    const int i = (int)(28 * w) - 4 + (int)lane;
-                    const bool act = lane >= 4 && i < (int)nh;
+                    const int i = (int)(WIN * w) - OWN + (int)lane;
+                    const bool act = lane >= OWN && i < (int)nh;
                     const uint32_t p = cur.pp & 0x7fffu;
-                    uint32_t rec[OWN_CAP + DICT_CAP];
+                    uint32_t rec[OWN + DICT_CAP];
                     uint32_t mask = 0;
 #pragma unroll
-                    for (int d = 1; d <= OWN_CAP; d++) {
+                    for (int d = 1; d <= OWN; d++) {
                         const uint32_t ppq = __shfl_up_sync(0xffffffffu, cur.pp, d);
                         const uint32_t vq = __shfl_up_sync(0xffffffffu, cur.v, d);
                         // same four bytes (hence same bucket, earlier position), different byte before: a run starts here
@@ -556,8 +564,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                             const uint32_t j = c[u] & 0x7fffu;
                             if (act && (int32_t)c[u] < 0 && (x & 0x7f800000u) == 0 && (x & 0x007f8000u) != 0 &&
                                 p + dlen - j <= (uint32_t)WSIZE)
-                                mask |= 16u << u;
-                            rec[OWN_CAP + u] = p | 0x8000u | (j << 16);
+                                mask |= (1u << OWN) << u;
+                            rec[OWN + u] = p | 0x8000u | (j << 16);
                         }
                     }
                     if (__any_sync(0xffffffffu, mask != 0)) {
@@ -571,7 +579,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         }
                         uint32_t o = pcnt + inc - c;
 #pragma unroll
-                        for (int sl = 0; sl < OWN_CAP + DICT_CAP; sl++)
+                        for (int sl = 0; sl < OWN + DICT_CAP; sl++)
                             if ((mask >> sl) & 1u) plist[o++] = rec[sl];
                         pcnt += __shfl_sync(0xffffffffu, inc, 31);
                         __syncwarp();
@@ -1780,8 +1788,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
 
     const size_t sm_parse[N_CLASS] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_MEDIUM, false), parse_smem(NMAX_LARGE, false)};
     const size_t sm_huff = sizeof(HuffSm) * HUFF_WARPS;
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<RS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[0]));
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[2]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<RS_SMALL, OWN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[0]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5, OWN_MEDIUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[1]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5, OWN_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[2]));
     HMSE_CUDA(ctx, cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_huff));
     const uint32_t nmax_c[N_CLASS] = {NMAX_SMALL, NMAX_MEDIUM, NMAX_LARGE};
     const uint32_t batch_c[N_CLASS] = {BATCH_SMALL, BATCH_MEDIUM, BATCH_LARGE};
@@ -1915,8 +1924,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             const uint32_t jobs = a.job1 - a.job0;
             KL(ctx);
             PARSE_EV(0);
-            if (c == 0) parse_kernel<RS_SMALL><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
-            else parse_kernel<5><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            if (c == 0) parse_kernel<RS_SMALL, OWN_SMALL><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            else if (c == 1) parse_kernel<5, OWN_MEDIUM><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            else parse_kernel<5, OWN_LARGE><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
             PARSE_EV(1);
             if (level != 0) {
                 const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
@@ -1950,7 +1960,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             long_dict_kernel<<<jobs < (uint32_t)ctx->sm_count ? jobs : (uint32_t)ctx->sm_count, 1024, 0, st>>>(a);
             KL(ctx);
             PARSE_EV(0);
-            parse_kernel<5><<<jobs < ctas_c[2] ? jobs : ctas_c[2], T_PARSE, sm_parse[2], st>>>(a);
+            parse_kernel<5, OWN_LARGE><<<jobs < ctas_c[2] ? jobs : ctas_c[2], T_PARSE, sm_parse[2], st>>>(a);
             PARSE_EV(1);
             const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
             KL(ctx);

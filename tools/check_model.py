@@ -23,13 +23,16 @@ def main():
     sizes = np.diff(np.asarray(offs).astype(np.int64))
     zdn = np.frombuffer(zd, dtype=np.uint8)
     out = np.zeros(70000, dtype=np.uint8)
-    pr = Params(hash_bytes=4, chain_own=4, chain_dict=4, lazy=1, too_far=0, dict_hash_bits=15, mode=2, min_len=0)
+    # own-chunk candidates follow the size class of parse_kernel (OWN_SMALL / OWN_MEDIUM / OWN_LARGE in csrc/deflate.cu)
+    prs = {own: Params(hash_bytes=4, chain_own=own, chain_dict=4, lazy=1, too_far=0, dict_hash_bits=15, mode=2, min_len=0)
+           for own in (2, 3, 4)}
     st = (C.c_uint32 * 8)()
     starts = np.concatenate([[0], np.asarray(cuts)[:-1]]).astype(np.int64)
     bad = 0
     tot_g = tot_m = 0
     for k, (s, e) in enumerate(zip(starts.tolist(), np.asarray(cuts).astype(np.int64).tolist())):
         ch = np.ascontiguousarray(data[s:e])
+        pr = prs[2 if e - s <= 12288 else 3 if e - s <= 20480 else 4]
         r = lib.model_compress(ch.ctypes.data, e - s, zdn.ctypes.data, len(zd), C.byref(pr), out.ctypes.data, out.size, st)
         tot_g += int(sizes[k]); tot_m += int(r)
         if r != sizes[k]:
