@@ -442,8 +442,10 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 if (others) s_tmp16[first + smaller] = (uint16_t)p;
                 return others != 0;
             };
-            if (t == 0) sm->n_big = 0;   // list length
-            __syncthreads();
+            // every warp keeps its own list (a shared list head would serialise the sixteen warps on one atomic)
+            constexpr uint32_t WCAP = LIST_CAP / (T_PARSE / 32);
+            uint16_t* wlist = s_list + warp * WCAP;
+            uint32_t wcnt = 0;   // warp-uniform
             {
                 uint32_t k = 0;
                 for (uint32_t ib = warp * 32; ib < nh; ib += T, k++) {   // warp-uniform trip count
@@ -455,25 +457,21 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         cand = (ql >> TILE_SHIFT) == tile || (qr >> TILE_SHIFT) == tile;
                     }
                     const uint32_t b = __ballot_sync(0xffffffffu, cand);
-                    if (b) {
-                        uint32_t base = 0;
-                        if (lane == 0) base = atomicAdd(&sm->n_big, (uint32_t)__popc(b));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (cand) {
-                            const uint32_t slot = base + __popc(b & ((1u << lane) - 1));
-                            if (slot < LIST_CAP) s_list[slot] = (uint16_t)i;
-                            else if (fix_member(i)) moved |= 1ull << k;   // (only on highly repetitive chunks)
-                        }
+                    if (cand) {
+                        const uint32_t slot = wcnt + __popc(b & ((1u << lane) - 1));
+                        if (slot < WCAP) wlist[slot] = (uint16_t)i;
+                        else if (fix_member(i)) moved |= 1ull << k;   // (only on highly repetitive chunks)
                     }
+                    wcnt += __popc(b);
                 }
             }
-            __syncthreads();
-            const uint32_t n_list = sm->n_big < LIST_CAP ? sm->n_big : LIST_CAP;
-            for (uint32_t j = t; j < n_list; j += T)
-                if (fix_member(s_list[j])) s_list[j] |= 0x8000u;
-            __syncthreads();
-            for (uint32_t j = t; j < n_list; j += T) {
-                const uint32_t e = s_list[j];
+            __syncwarp();
+            const uint32_t n_list = wcnt < WCAP ? wcnt : WCAP;
+            for (uint32_t j = lane; j < n_list; j += 32)
+                if (fix_member(wlist[j])) wlist[j] |= 0x8000u;
+            __syncthreads();   // every group has been read before any element moves
+            for (uint32_t j = lane; j < n_list; j += 32) {
+                const uint32_t e = wlist[j];
                 if (e & 0x8000u) s_sorted[e & 0x7fffu] = s_tmp16[e & 0x7fffu];
             }
             for (uint64_t mm = moved; mm; mm &= mm - 1) {
