@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gb", type=float, default=10.0, help="bytes per GPU per step, in GB (1e9)")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
-    ap.add_argument("--piece-mib", type=int, default=1024, help="piece size of the streaming end-to-end path")
+    ap.add_argument("--piece-mib", type=int, default=2048, help="piece size of the streaming end-to-end path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-size inflate + digest round-trip check")
@@ -424,14 +424,15 @@ def run_ours(args):
             del d, res, cuts, starts, lens
             torch.cuda.empty_cache()
             stream_pipe = hmse_b200.IngestStream(ctx, cfg, zd, piece_bytes=args.piece_mib << 20)
-            api = ("hmse_b200.IngestStream.run(pinned host buffer): %d MiB pieces, host->device copy of piece k+1, pipeline "
-                   "on piece k and device->host copy of the results of piece k-1 (cuts, digests, canon, offsets, "
-                   "compressed blob) overlap on three CUDA streams" % args.piece_mib)
+            api = ("hmse_b200.IngestStream.run_many(pinned host buffers, one per step): %d MiB pieces, host->device copy of "
+                   "piece k+1, pipeline on piece k and device->host copy of the results of piece k-1 (cuts, digests, canon, "
+                   "offsets, compressed blob) overlap on three CUDA streams; the next step's input is copied in behind the "
+                   "current step's (two device input buffers)" % args.piece_mib)
 
-            def e2e_step():
+            def e2e_steps(k):
                 nonlocal d2h
-                r = stream_pipe.run(host_in, host_blob_cap=n_avail // 2 + (1 << 20))
-                d2h = r.d2h_bytes
+                for r in stream_pipe.run_many([host_in] * k, host_blob_cap=n_avail // 2 + (1 << 20)):
+                    d2h = r.d2h_bytes
         else:
             host_out = pipe.host_buffers(n_avail)
             api = ("hmse_b200.ShardedIngest.run_batches(pinned host shard buffers, host=pinned result buffers): every step's "
@@ -445,10 +446,6 @@ def run_ours(args):
                     d2h = r.d2h_bytes
 
         k_e2e = max(1, min(args.steps, 5))
-        if world == 1:
-            def e2e_steps(k):
-                for _ in range(k):
-                    e2e_step()
         e2e_steps(1)
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -135,15 +135,18 @@ class IngestStream(Ingest):
         self.piece = int(piece_bytes)
         self.s_h2d = torch.cuda.Stream(ctx.tdev)
         self.s_d2h = torch.cuda.Stream(ctx.tdev)
-        self._dbuf = None
+        self._dbufs = [None, None]   # device input buffers: the stream being processed and the one prefetched behind it
+        self._last_slot = 1
+        self._pending = []           # streams whose host->device copies are already queued (prefetch / run_many)
         self._dig = None
         self._host = None
         self._stage = [None, None]   # device blobs of the pieces in flight (double buffer)
         self.trace = None   # set to a list to collect (label, host ms since run() began) marks
         self.timing_hook = None   # called once per piece after its kernels are queued (bench: per-stage event spans)
 
-    def schedule(self, n: int):
-        """Piece end offsets: sizes ramp x4 from piece/16 up to piece, and down again at the end."""
+    def schedule(self, n: int, ramp_up: bool = True):
+        """Piece end offsets: sizes ramp x4 from piece/16 up to piece (unless the input is already arriving: a
+        prefetched stream), and down again at the end."""
         lo = max(4 * self.cdc.max_size, (self.piece // 16) & ~15)
         up, s = [], lo
         while s < self.piece:
@@ -154,7 +157,7 @@ class IngestStream(Ingest):
             step = (-(-n // k) + 15) & ~15
             return [min(n, (i + 1) * step) for i in range(k)]
         ends, pos = [], 0
-        for s in up:
+        for s in (up if ramp_up else []):
             pos += s
             ends.append(pos)
         tail = sum(up)
@@ -164,7 +167,7 @@ class IngestStream(Ingest):
         rest = n - tail - pos
         if rest > 0:
             pos += (rest + 15) & ~15 if rest % 16 and pos + ((rest + 15) & ~15) <= n - tail else rest & ~15
-            if pos > ends[-1]:
+            if not ends or pos > ends[-1]:
                 ends.append(pos)
         for s in reversed(up):
             pos = n if s == up[0] else min(n, pos + s)
@@ -174,9 +177,6 @@ class IngestStream(Ingest):
 
     def _buffers(self, n: int, host_blob_cap: int):
         cap_chunks = n // self.cdc.min_size + 2
-        if self._dbuf is None or self._dbuf.numel() < n + 64:
-            self._dbuf = None
-            self._dbuf = self.ctx.empty(n + 64, torch.uint8)
         if self._dig is None or self._dig.numel() < cap_chunks * 32:
             self._dig = self.ctx.empty(cap_chunks * 32, torch.uint8)
         h = self._host
@@ -188,6 +188,54 @@ class IngestStream(Ingest):
                 "offsets": torch.empty(cap_chunks + 1, dtype=torch.int64, pin_memory=True),
                 "blob": torch.empty(host_blob_cap, dtype=torch.uint8, pin_memory=True)}
         return cap_chunks, h
+
+    def _queue_in(self, host_in: torch.Tensor, ramp_up: bool = True):
+        """Queues every host->device copy of one stream (piece by piece, an event per piece) on the copy stream, into
+        the device input buffer that the previous stream does not occupy."""
+        ctx = self.ctx
+        n = host_in.numel()
+        slot = self._last_slot ^ 1
+        self._last_slot = slot
+        if self._dbufs[slot] is None or self._dbufs[slot].numel() < n + 64:
+            self._dbufs[slot] = None
+            self._dbufs[slot] = ctx.empty(n + 64, torch.uint8)
+        dbuf = self._dbufs[slot]
+        ends = self.schedule(n, ramp_up) if n else [0]
+        self.s_h2d.wait_stream(torch.cuda.current_stream(ctx.device))
+        ev_in = []
+        with torch.cuda.stream(self.s_h2d):
+            a = 0
+            for b in ends:
+                if b > a:
+                    dbuf[a:b].copy_(host_in[a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self.s_h2d)
+                ev_in.append(e)
+                a = b
+        return {"key": (host_in.data_ptr(), n), "dbuf": dbuf, "ends": ends, "ev_in": ev_in}
+
+    def prefetch(self, host_in: torch.Tensor, ramp_up: bool = False) -> None:
+        """Starts copying the NEXT stream to the device behind the copies of the current one (at most one stream ahead):
+        the following run(host_in) finds its input arriving or already there, so its piece schedule needs no ramp."""
+        if len(self._pending) >= 2:
+            raise RuntimeError("at most one stream can be prefetched ahead of the running one")
+        self._pending.append(self._queue_in(host_in, ramp_up))
+
+    def run_many(self, host_streams, host_blob_cap: Optional[int] = None, compress: bool = True):
+        """A sequence of streams in pinned host memory: generator of HostIngestResult, each valid until the next is
+        requested.  The input of stream k+1 is copied in while stream k is processed (its copies queue up behind
+        stream k's), so only the first stream pays for the ramp of the piece schedule."""
+        it = iter(host_streams)
+        cur_h = next(it, None)
+        if cur_h is None:
+            return
+        self.prefetch(cur_h, ramp_up=True)
+        while cur_h is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                self.prefetch(nxt)
+            yield self.run(cur_h, host_blob_cap, compress)
+            cur_h = nxt
 
     def run(self, host_in: torch.Tensor, host_blob_cap: Optional[int] = None, compress: bool = True) -> HostIngestResult:
         import queue
@@ -205,22 +253,18 @@ class IngestStream(Ingest):
         if host_blob_cap is None:
             host_blob_cap = n + n // 64 + (1 << 20)
         cap_chunks, host = self._buffers(n, host_blob_cap)
-        dbuf, dig = self._dbuf, self._dig
+        dig = self._dig
         cur = torch.cuda.current_stream(ctx.device)
-        ends = self.schedule(n) if n else [0]
+        # every host->device copy is queued up front: the copy engine runs ahead of the kernels (already done when this
+        # stream was prefetched)
+        if self._pending and self._pending[0]["key"] == (host_in.data_ptr(), n):
+            qin = self._pending.pop(0)
+        else:
+            if self._pending:
+                raise RuntimeError("run() must be given the prefetched stream first")
+            qin = self._queue_in(host_in)
+        dbuf, ends, ev_in = qin["dbuf"], qin["ends"], qin["ev_in"]
         overlap = self.overlap and compress and len(ends) > 1
-        # every host->device copy is queued up front: the copy engine runs ahead of the kernels
-        self.s_h2d.wait_stream(cur)
-        ev_in = []
-        with torch.cuda.stream(self.s_h2d):
-            a = 0
-            for b in ends:
-                if b > a:
-                    dbuf[a:b].copy_(host_in[a:b], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(self.s_h2d)
-                ev_in.append(e)
-                a = b
         mark("copies queued")
         host["offsets"][0] = 0
 

@@ -88,3 +88,32 @@ def test_dedup_append_matches_oracle(ctx):
     # contract errors: wrong n_prev, over capacity
     assert lib.hmse_dedup_append(ctx.h, d.data_ptr(), 17, 1, canon.data_ptr(), first.data_ptr(), ctx.stream) != 0
     assert lib.hmse_dedup_append(ctx.h, d.data_ptr(), 5000, 1 << 20, canon.data_ptr(), first.data_ptr(), ctx.stream) != 0
+
+
+def test_run_many_prefetch_equals_single_runs(ctx, corpus8):
+    """IngestStream.run_many: the next stream's input is copied in behind the current one's (two device input
+    buffers); every result equals a plain run of that stream, in order, including streams of different sizes."""
+    import torch
+    import hmse_b200
+    from oracle import corpus
+    zd = corpus.zdict()
+    streams = [corpus8[:3 << 20], corpus8[1 << 20:(5 << 20) + 777], corpus8[:4096], corpus8[2 << 20:6 << 20]]
+    hosts = [torch.from_numpy(s.copy()).pin_memory() for s in streams]
+    st = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=512 << 10)
+    ref = hmse_b200.IngestStream(ctx, hmse_b200.CDCConfig(), zd, piece_bytes=512 << 10)
+    k = 0
+    for res in st.run_many(hosts):
+        want = ref.run(hosts[k])
+        assert np.array_equal(res.cuts.numpy(), want.cuts.numpy()) and np.array_equal(res.canon.numpy(), want.canon.numpy())
+        assert np.array_equal(res.digests.numpy(), want.digests.numpy())
+        assert np.array_equal(res.offsets.numpy(), want.offsets.numpy()) and np.array_equal(res.blob.numpy(), want.blob.numpy())
+        k += 1
+    assert k == len(hosts)
+    # a plain run still works afterwards, and prefetching two streams ahead is refused
+    assert np.array_equal(st.run(hosts[0]).cuts.numpy(), ref.run(hosts[0]).cuts.numpy())
+    st.prefetch(hosts[1])
+    st.prefetch(hosts[2])
+    with pytest.raises(RuntimeError):
+        st.prefetch(hosts[3])
+    assert np.array_equal(st.run(hosts[1]).blob.numpy(), ref.run(hosts[1]).blob.numpy())
+    assert np.array_equal(st.run(hosts[2]).blob.numpy(), ref.run(hosts[2]).blob.numpy())
