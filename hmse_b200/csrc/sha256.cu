@@ -23,7 +23,17 @@ __constant__ uint32_t K256[64] = {
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
 
-__device__ __forceinline__ void sha256_block(uint32_t (&H)[8], uint32_t (&W)[16]) {
+// a + b as a * one + b with `one` a kernel argument (always 1): ptxas cannot fold the multiply, so the addition issues
+// as an IMAD on the fma pipe.  The block function is otherwise all alu-pipe work (21.5 alu vs 1.9 fma instructions per
+// round, ncu: alu pipe 84 % busy, fma 4 %), and both pipes issue one warp instruction per two cycles.
+__device__ __forceinline__ uint32_t madd(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+
+template <int FMA_ADDS>
+__device__ __forceinline__ void sha256_block(uint32_t (&H)[8], uint32_t (&W)[16], uint32_t one) {
     uint32_t a = H[0], b = H[1], c = H[2], d = H[3], e = H[4], f = H[5], g = H[6], h = H[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
@@ -31,31 +41,44 @@ __device__ __forceinline__ void sha256_block(uint32_t (&H)[8], uint32_t (&W)[16]
             uint32_t w15 = W[(i + 1) & 15], w2 = W[(i + 14) & 15];
             uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
             uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-            W[i & 15] = W[i & 15] + s0 + W[(i + 9) & 15] + s1;
+            if (FMA_ADDS >= 1) W[i & 15] = madd(madd(W[i & 15], s0, one), madd(W[(i + 9) & 15], s1, one), one);
+            else W[i & 15] = W[i & 15] + s0 + W[(i + 9) & 15] + s1;
         }
         uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
         uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + K256[i] + W[i & 15];
         uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
+        uint32_t t1, t2, en, an;
+        if (FMA_ADDS >= 2) {
+            const uint32_t x = madd(h, W[i & 15] + K256[i], one);   // off the critical path: h and W are old values
+            t1 = madd(madd(S1, ch, one), x, one);
+            t2 = madd(S0, mj, one);
+            en = madd(d, t1, one);
+            an = madd(t1, t2, one);
+        } else {
+            t1 = h + S1 + ch + K256[i] + W[i & 15];
+            t2 = S0 + mj;
+            en = d + t1;
+            an = t1 + t2;
+        }
         h = g;
         g = f;
         f = e;
-        e = d + t1;
+        e = en;
         d = c;
         c = b;
         b = a;
-        a = t1 + t2;
+        a = an;
     }
     H[0] += a; H[1] += b; H[2] += c; H[3] += d; H[4] += e; H[5] += f; H[6] += g; H[7] += h;
 }
 
 constexpr int SHA_THREADS = 128;
 
+template <int FMA_ADDS>
 __global__ void __launch_bounds__(SHA_THREADS)
 sha256_kernel(const uint8_t* __restrict__ data, uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t n_chunks,
-              uint8_t* __restrict__ digests, unsigned long long* __restrict__ counter) {
+              uint8_t* __restrict__ digests, unsigned long long* __restrict__ counter, uint32_t one) {
     uint32_t H[8], W[16];
     uint64_t j = 0, s = 0, len = 0, blk = 0, nblk = 0;
     bool have = false, done = false;
@@ -110,7 +133,7 @@ sha256_kernel(const uint8_t* __restrict__ data, uint64_t start0, const uint64_t*
                     W[15] = (uint32_t)bits;
                 }
             }
-            sha256_block(H, W);
+            sha256_block<FMA_ADDS>(H, W, one);
             blk++;
             if (blk == nblk) {
                 uint4* o = reinterpret_cast<uint4*>(digests + (j << 5));
@@ -142,7 +165,9 @@ HMSE_API int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, 
     if (blocks > max_blocks) blocks = max_blocks;
     HT_BEGIN(ctx, HT_SHA, st);
     KL(ctx);
-    sha256_kernel<<<(unsigned)blocks, SHA_THREADS, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_digests, counter);
+    // FMA_ADDS = 2 (message schedule and round additions as IMADs) measured on B200: 14.6 -> 13.1 ms per 10 GB
+    // (687 -> 763 GB/s); moving the W + K addition as well (a second IMAD) was slower again (13.5 ms).
+    sha256_kernel<2><<<(unsigned)blocks, SHA_THREADS, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_digests, counter, 1u);
     HMSE_LAUNCH_CHECK(ctx);
     HT_END(ctx, HT_SHA, st);
     return HMSE_OK;
