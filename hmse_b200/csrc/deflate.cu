@@ -321,12 +321,20 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;
             for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
             sb %= 65521u;
-            uint32_t tot_a, tot_b;
-            block_excl_scan(sa, sm->warp_tmp, &tot_a);   // (these also order the staging before its readers)
-            block_excl_scan(sb, sm->warp_tmp, &tot_b);
-            if (t == 0) {
-                sm->adler_a = (1u + tot_a) % 65521u;
-                sm->adler_b = (n % 65521u + tot_b) % 65521u;
+            // only the two block totals are needed: one REDUX per warp, sixteen partial sums in shared memory
+            const uint32_t wa = __reduce_add_sync(0xffffffffu, sa), wb = __reduce_add_sync(0xffffffffu, sb);
+            if (lane == 0) {
+                sm->warp_tmp[warp] = wa;        // <= 16 x 512 x 1020
+                sm->warp_tmp[16 + warp] = wb;   // < 32 x 65521
+            }
+            __syncthreads();                    // (also orders the staging before its readers)
+            if (warp == 0) {
+                const uint32_t tot_a = __reduce_add_sync(0xffffffffu, lane < nwarps ? sm->warp_tmp[lane] : 0u);
+                const uint32_t tot_b = __reduce_add_sync(0xffffffffu, lane < nwarps ? sm->warp_tmp[16 + lane] : 0u);
+                if (lane == 0) {
+                    sm->adler_a = (1u + tot_a) % 65521u;
+                    sm->adler_b = (n % 65521u + tot_b) % 65521u;
+                }
             }
         }
         __syncthreads();
