@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 auto extend_pairs = [&](uint32_t first, uint32_t count) {   // phase B on plist[first .. first+count)
                     if (lane < count) {
                         const uint32_t rec = plist[first + lane];
-                        const uint32_t p = rec & 0x7fffu, src = rec >> 16;
+                        const uint32_t p = rec & 0x7fffu, src = (rec >> 16) & 0x7fffu;
                         const bool isd = (rec & 0x8000u) != 0;
                         uint32_t lim = n - p, dist = p - src;
                         const uint32_t* sw = s_data32;
@@ -558,22 +558,26 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         const uint32_t ppq = __shfl_up_sync(0xffffffffu, cur.pp, d);
                         const uint32_t vq = __shfl_up_sync(0xffffffffu, cur.v, d);
                         // same four bytes (hence same bucket, earlier position), different byte before: a run starts here
-                        if (act && vq == cur.v && ((ppq ^ cur.pp) >> 16) != 0 && ppq != 0xffffffffu) mask |= 1u << (d - 1);
+                        if (vq == cur.v && ((ppq ^ cur.pp) >> 16) != 0 && ppq != 0xffffffffu) mask |= 1u << (d - 1);
                         rec[d - 1] = p | (ppq << 16);
                     }
                     if (use_dict) {
-                        const uint32_t my = dict_tag23(cur.v) | ((cur.pp >> 16) << 15);
+                        // record: valid << 31 | tag << 23 | prev << 15 | pos.  x = record ^ (1 << 31 | my tag | my prev):
+                        // valid, same tag and a different previous byte  <=>  0x8000 <= x < 0x800000 (one subtract, one
+                        // compare); inside the window  <=>  pos + WSIZE >= p + dlen.  The pair record takes its source
+                        // half straight from the bucket record (bit 15 of it is masked off by the reader).
+                        const uint32_t myv = 0x80000000u | dict_tag23(cur.v) | ((cur.pp >> 16) << 15);
+                        const uint32_t pq = p | 0x8000u;
+                        const uint32_t thr = p + dlen > (uint32_t)WSIZE ? p + dlen - (uint32_t)WSIZE : 0u;
                         const uint32_t c[4] = {cur.bk.x, cur.bk.y, cur.bk.z, cur.bk.w};
 #pragma unroll
                         for (int u = 0; u < DICT_CAP; u++) {
-                            const uint32_t x = c[u] ^ my;   // valid, same tag, different previous byte, inside the window
-                            const uint32_t j = c[u] & 0x7fffu;
-                            if (act && (int32_t)c[u] < 0 && (x & 0x7f800000u) == 0 && (x & 0x007f8000u) != 0 &&
-                                p + dlen - j <= (uint32_t)WSIZE)
-                                mask |= (1u << OWN) << u;
-                            rec[OWN + u] = p | 0x8000u | (j << 16);
+                            const uint32_t x = c[u] ^ myv;
+                            if ((x - 0x8000u) < 0x7F8000u && (c[u] & 0x7fffu) >= thr) mask |= (1u << OWN) << u;
+                            rec[OWN + u] = __byte_perm(pq, c[u], 0x5410);
                         }
                     }
+                    if (!act) mask = 0;
                     if (__any_sync(0xffffffffu, mask != 0)) {
                         // compaction: exclusive scan of the per-lane pair counts
                         const uint32_t c = __popc(mask);
