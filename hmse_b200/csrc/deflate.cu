@@ -506,11 +506,12 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 uint32_t* plist = s_cnt32 + warp * PAIR_CAP;   // the bucket table is dead: E is not needed to walk s_sorted
                 uint32_t pcnt = 0;                             // warp-uniform
                 const uint32_t nwin = (nh + WIN - 1) / WIN;
-                struct StA { uint32_t pp, v; uint4 bk; };
-                // pp = position | previous byte << 16; lanes outside the index range carry pp = ~0
+                struct StA { uint32_t sig; uint4 bk; };
+                // sig = 1 << 31 | tag << 23 | previous byte << 15 | position - the layout of a dictionary bucket record, with
+                // tag = eight bits of the hash product below the bucket bits; lanes outside the index range carry 0
                 auto stageA = [&](uint32_t w) {
                     StA r;
-                    r.pp = 0xffffffffu; r.v = 0; r.bk = make_uint4(0, 0, 0, 0);
+                    r.sig = 0; r.bk = make_uint4(0, 0, 0, 0);
                     const int i = (int)(WIN * w) - OWN + (int)lane;
                     if (w < nwin && i >= 0 && i < (int)nh) {
                         const uint32_t p = s_sorted[i];
@@ -519,10 +520,10 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         const uint32_t pm = p ? p - 1 : 0u;
                         const uint32_t w0 = s_data32[pm >> 2], w1 = s_data32[(pm >> 2) + 1];
                         const uint32_t sh8 = (pm & 3) * 8;
-                        const uint32_t lo5 = __funnelshift_r(w0, w1, sh8);          // bytes pm .. pm+3
-                        r.v = p ? __funnelshift_r(lo5, w1 >> sh8, 8) : lo5;        // bytes p .. p+3
-                        r.pp = p | ((p ? (lo5 & 0xffu) : CHUNK_PREV0) << 16);
-                        if (use_dict && lane >= OWN) r.bk = __ldg(&dict->bk4[hash_dict(r.v)]);
+                        const uint32_t lo5 = __funnelshift_r(w0, w1, sh8);                    // bytes pm .. pm+3
+                        const uint32_t v = p ? __funnelshift_r(lo5, w1 >> sh8, 8) : lo5;     // bytes p .. p+3
+                        r.sig = 0x80000000u | dict_tag23(v) | ((p ? (lo5 & 0xffu) : CHUNK_PREV0) << 15) | p;
+                        if (use_dict && lane >= OWN) r.bk = __ldg(&dict->bk4[hash_dict(v)]);
                     }
                     return r;
                 };
@@ -550,30 +551,29 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
 
                     const int i = (int)(WIN * w) - OWN + (int)lane;
                     const bool act = lane >= OWN && i < (int)nh;
-                    const uint32_t p = cur.pp & 0x7fffu;
+                    const uint32_t p = cur.sig & 0x7fffu;
                     uint32_t rec[OWN + DICT_CAP];
                     uint32_t mask = 0;
+                    // A candidate (own: the sig of a preceding lane; dictionary: a bucket record) starts a run here when
+                    // x = candidate ^ sig shows both valid, the same tag and a different previous byte, i.e.
+                    // 0x8000 <= x < 0x800000: one subtract and one compare.  The tag is only a filter (same bucket and
+                    // same tag, different bytes: 1 in 256): phase B compares the real bytes from the first one.
+                    // The pair record takes its source half straight from the candidate (bit 15 of that half is the low
+                    // bit of its previous byte and is masked off by the reader).
 #pragma unroll
                     for (int d = 1; d <= OWN; d++) {
-                        const uint32_t ppq = __shfl_up_sync(0xffffffffu, cur.pp, d);
-                        const uint32_t vq = __shfl_up_sync(0xffffffffu, cur.v, d);
-                        // same four bytes (hence same bucket, earlier position), different byte before: a run starts here
-                        if (vq == cur.v && ((ppq ^ cur.pp) >> 16) != 0 && ppq != 0xffffffffu) mask |= 1u << (d - 1);
-                        rec[d - 1] = p | (ppq << 16);
+                        const uint32_t sq = __shfl_up_sync(0xffffffffu, cur.sig, d);
+                        if (((sq ^ cur.sig) - 0x8000u) < 0x7F8000u) mask |= 1u << (d - 1);
+                        rec[d - 1] = __byte_perm(p, sq, 0x5410);
                     }
                     if (use_dict) {
-                        // record: valid << 31 | tag << 23 | prev << 15 | pos.  x = record ^ (1 << 31 | my tag | my prev):
-                        // valid, same tag and a different previous byte  <=>  0x8000 <= x < 0x800000 (one subtract, one
-                        // compare); inside the window  <=>  pos + WSIZE >= p + dlen.  The pair record takes its source
-                        // half straight from the bucket record (bit 15 of it is masked off by the reader).
-                        const uint32_t myv = 0x80000000u | dict_tag23(cur.v) | ((cur.pp >> 16) << 15);
+                        // inside the window  <=>  pos + WSIZE >= p + dlen
                         const uint32_t pq = p | 0x8000u;
                         const uint32_t thr = p + dlen > (uint32_t)WSIZE ? p + dlen - (uint32_t)WSIZE : 0u;
                         const uint32_t c[4] = {cur.bk.x, cur.bk.y, cur.bk.z, cur.bk.w};
 #pragma unroll
                         for (int u = 0; u < DICT_CAP; u++) {
-                            const uint32_t x = c[u] ^ myv;
-                            if ((x - 0x8000u) < 0x7F8000u && (c[u] & 0x7fffu) >= thr) mask |= (1u << OWN) << u;
+                            if (((c[u] ^ cur.sig) - 0x8000u) < 0x7F8000u && (c[u] & 0x7fffu) >= thr) mask |= (1u << OWN) << u;
                             rec[OWN + u] = __byte_perm(pq, c[u], 0x5410);
                         }
                     }
