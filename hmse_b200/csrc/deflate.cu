@@ -136,7 +136,7 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t hist[REC_WORDS];
     uint16_t bentry[32];
     uint32_t warp_tmp[40];
-    uint32_t job, n_big;
+    uint32_t job, pad0;
     uint32_t adler_a, adler_b;
 };
 

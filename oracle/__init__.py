@@ -35,5 +35,5 @@ from .sha import digest, dedup  # noqa: F401
 from .deflate import compress, inflate_all, make_zdict  # noqa: F401
 from .minhash import (murmur3_32, minhash, minhash_c, band_keys, buckets,  # noqa: F401
                       similarity)
-from .deltacode import delta_bases, delta_encode, delta_apply, delta, lsh_heads  # noqa: F401
+from .deltacode import delta_bases, delta_encode, delta_encode_naive, delta_apply, delta, lsh_heads  # noqa: F401
 from . import archive, corpus  # noqa: F401

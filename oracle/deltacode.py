@@ -160,6 +160,45 @@ def delta_encode(target, base):
     return bytes(out) if len(out) <= cap else None
 
 
+def delta_encode_naive(target, base):
+    """The same encoder as a literal byte-at-a-time transcription of the module docstring (pure Python, no NumPy):
+    ground truth for delta_encode, like chunk_naive is for chunk."""
+    T, B = bytes(target), bytes(base)
+    n, nb = len(T), len(B)
+    if n == 0 or n > MAX_LEN or nb > MAX_LEN:
+        return None
+    M64 = (1 << 64) - 1
+
+    def h(buf, i):
+        return ((int.from_bytes(buf[i:i + 8], "little") * HASH_MUL) & M64) >> (64 - HASH_BITS)
+
+    H = {}
+    for q in range(nb - 7):
+        H.setdefault(h(B, q), q)          # positions ascend: the first one seen is the smallest
+    out = bytearray()
+    p = expect = 0
+    s = 0
+    while s + 8 <= n:
+        q = H.get(h(T, s))
+        if q is None or B[q:q + 8] != T[s:s + 8]:
+            s += 1
+            continue
+        while s > p and q > 0 and T[s - 1] == B[q - 1]:
+            s -= 1
+            q -= 1
+        L = 0
+        while s + L < n and q + L < nb and T[s + L] == B[q + L]:
+            L += 1
+        if s > p:
+            out += _varint((s - p) << 1) + T[p:s]
+        out += _varint((L << 1) | 1) + _varint(_zigzag(q - expect))
+        expect = q + L
+        p = s = s + L
+    if p < n:
+        out += _varint((n - p) << 1) + T[p:]
+    return bytes(out) if len(out) * 5 <= n else None
+
+
 def delta_apply(delta: bytes, base: bytes, n: int) -> bytes:
     """Reconstructs the n-byte target; raises ValueError on a malformed delta."""
     out = bytearray()

@@ -224,3 +224,36 @@ def test_oracle_matches_committed_delta_golden():
     assert [[int(i), int(base[i])] for i in np.flatnonzero(base >= 0)] == g["kept"]
     assert hashlib.sha256(blob.tobytes()).hexdigest() == g["blob_sha256"] and blob.size == g["delta_bytes"]
     assert hashlib.sha256(offs.astype("<u8").tobytes()).hexdigest() == g["offsets_sha256"]
+
+
+def test_vectorised_encoder_equals_the_literal_byte_loop():
+    """delta_encode (NumPy) against delta_encode_naive (a literal transcription of the format definition) on edited
+    text, binary and low-entropy pairs, including rejected ones."""
+    rng = np.random.default_rng(11)
+    text = oracle.corpus.generate(200000).tobytes()
+    kept = 0
+    for k in range(60):
+        n = int(rng.integers(1, 9000))
+        kind = k % 3
+        if kind == 0:
+            off = int(rng.integers(0, len(text) - n))
+            b = text[off:off + n]
+        elif kind == 1:
+            b = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        else:
+            b = bytes(rng.integers(97, 99, n, dtype=np.uint8))
+        t = bytearray(b)
+        for _ in range(int(rng.integers(0, 10))):
+            pos = int(rng.integers(0, max(1, len(t))))
+            if rng.integers(0, 2):
+                t[pos:pos] = bytes(rng.integers(65, 91, int(rng.integers(1, 20)), dtype=np.uint8))
+            else:
+                del t[pos:pos + int(rng.integers(1, 20))]
+        t = bytes(t) or b"x"
+        a, c = D.delta_encode(t, b), D.delta_encode_naive(t, b)
+        assert a == c, (k, n, None if a is None else a[:12].hex(), None if c is None else c[:12].hex())
+        kept += a is not None
+    assert kept > 20
+    # the hand-assembled vectors hold for the literal loop too
+    base = bytes(range(256)) * 4
+    assert D.delta_encode_naive(base, base) == bytes([0x81, 0x10, 0x00])
