@@ -213,6 +213,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: hmse_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # pinned host buffers should live on the GPU's own NUMA node (matters for the end-to-end leg at N > 1)
+    numa = hmse_b200.sharding.bind_to_gpu_numa(local) if os.environ.get("HMSE_NO_NUMA_BIND") is None else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -475,7 +477,7 @@ def run_ours(args):
                            "chunks": int(tot_chunks), "unique_chunks": int(uniq_chunks),
                            "unique_bytes": int(sel_b), "compressed_bytes": int(out_b),
                            "compression_ratio_unique": (sel_b / out_b) if out_b else None},
-                "stages_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "verify": verify, "l4": l4, "gpu_launches": int(launches),
+                "stages_ms": stage_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "verify": verify, "l4": l4, "numa_bind": numa, "gpu_launches": int(launches),
                 "clocks": clocks}
         print(json.dumps(line))
     if dist is not None:
