@@ -2,7 +2,7 @@
 // difference, store delta only if size <= 20 % of original chunk"; flow README.md:1555-1570; Appendix A
 // README.md:2160-2198; op-list example README.md:1402-1412).  The spec names xdelta3 / bsdiff without a byte
 // format; the coding is the one oracle/deltacode.py defines and this file reproduces byte for byte:
-//   base selection  head(i,b) = first chunk of the bucket (band b, key) chunk i falls in; votes(i,j) = bands
+//   base selection  head(i,b) = first first-occurrence chunk of the bucket (band b, key) chunk i falls in; votes(i,j) = bands
 //                   whose head is j < i; root(i) = first occurrence with no j reaching min_votes;
 //                   base(i) = best-voted root (ties to the smaller id)  -> bases never chain
 //   delta           op* ; op = varint(len << 1 | kind) ; ADD: len literals ; COPY: varint(zigzag(q - expect))
@@ -25,7 +25,7 @@ constexpr int DT = 256;  // threads per encode CTA
 // Sorted (band, key, id) triples: the head of a bucket is its first triple.  Gallop back to the bucket start.
 __global__ void heads_kernel(const uint32_t* __restrict__ band, const uint64_t* __restrict__ key,
                              const uint64_t* __restrict__ id, uint64_t n_tr, uint32_t bands, uint64_t id_base,
-                             uint32_t* __restrict__ heads) {
+                             const uint8_t* __restrict__ is_first, uint32_t* __restrict__ heads) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n_tr) return;
     const uint32_t b = band[t];
@@ -45,7 +45,12 @@ __global__ void heads_kernel(const uint32_t* __restrict__ band, const uint64_t* 
         }
         start = hi;
     }
-    heads[(id[t] - id_base) * bands + b] = (uint32_t)(id[start] - id_base);
+    // only first occurrences are ever inserted into the index (README.md:1553-1556): skip duplicates at the front of
+    // the bucket (in one stream a duplicate is preceded by its first occurrence, so this loop does not run; it does on
+    // a shard whose duplicates have their first occurrence elsewhere).  No first occurrence at all: the chunk itself.
+    int64_t hd = start;
+    while (hd < t && !is_first[id[hd] - id_base]) hd++;
+    heads[(id[t] - id_base) * bands + b] = (uint32_t)(id[hd] - id_base);
 }
 
 // pass 0: root flags; pass 1: bases.  One warp per chunk, one lane per band (bands <= 32).
@@ -342,7 +347,8 @@ HMSE_API int hmse_delta_bases(hmse_ctx* ctx, const uint32_t* d_band, const uint6
     uint8_t* root = reinterpret_cast<uint8_t*>(heads + n * bands);
     HT_BEGIN(ctx, HT_DELTA, st);
     KL(ctx);
-    heads_kernel<<<(unsigned)div_up64(n * bands, 256), 256, 0, st>>>(d_band, d_key, d_id, n * bands, bands, id_base, heads);
+    heads_kernel<<<(unsigned)div_up64(n * bands, 256), 256, 0, st>>>(d_band, d_key, d_id, n * bands, bands, id_base, d_is_first,
+                                                                     heads);
     KL(ctx);
     votes_kernel<0><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(heads, n, bands, d_is_first, min_votes, root, d_base);
     KL(ctx);

@@ -47,22 +47,24 @@ class Ingest:
                                                       self.ctx.stream))
         return sel[:m.value]
 
-    def similarity_delta(self, d: torch.Tensor, cuts: torch.Tensor, first: torch.Tensor, sim: SimConfig, min_votes: int = 4):
+    def similarity_delta(self, d: torch.Tensor, cuts: torch.Tensor, first: torch.Tensor, sim: SimConfig, min_votes: int = 4,
+                         start0: int = 0):
         """The L4 stage (README.md:1553-1570): MinHash -> band keys -> buckets -> base selection -> delta coding with
-        the 20 % rule.  Returns (base int64[n], delta blob, delta offsets int64[n+1])."""
+        the 20 % rule.  Returns (base int64[n], delta blob, delta offsets int64[n+1]).  `start0`: offset of chunk 0
+        in `d` (a shard whose first owned chunk does not start at 0)."""
         ctx = self.ctx
         # Only first occurrences are hashed (the spec computes MinHash after the exact-dedup miss, README.md:1553-1556).
         # Duplicates never head a bucket (their first occurrence has the same keys and a smaller index), so selecting
         # bases among the first occurrences alone, in their compacted index space, gives the same bases.
         sel = self.select_first(first.view(torch.uint8))
         m = sel.numel()
-        keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim, select=sel), sim)
+        keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim, start0=start0, select=sel), sim)
         band, key, ids = ctx.lsh_buckets(keys)
         ones = torch.ones(m, dtype=torch.uint8, device=ctx.tdev)
         base_u = ctx.delta_bases(band, key, ids, m, sim.bands, ones, min_votes)
         base = torch.full((cuts.numel(),), -1, dtype=torch.int64, device=ctx.tdev)
         base[sel] = torch.where(base_u >= 0, sel[base_u.clamp(min=0)], base_u)
-        dblob, doffs = ctx.delta_encode(d, cuts, base)
+        dblob, doffs = ctx.delta_encode(d, cuts, base, start0=start0)
         return base, dblob, doffs
 
     def run(self, d: torch.Tensor, compress: bool = True, l4: Optional[SimConfig] = None, min_votes: int = 4) -> IngestResult:
@@ -429,9 +431,13 @@ class ShardedIngest(Ingest):
         self._stage = [None, None]
         self._in = [None, None]
 
-    def run(self, d: torch.Tensor, n_own: int, eof: bool, compress: bool = True, host=None, groups: int = 8):
+    def run(self, d: torch.Tensor, n_own: int, eof: bool, compress: bool = True, host=None, groups: int = 8,
+            l4: Optional[SimConfig] = None, min_votes: int = 4):
         """One shard.  With `host` (pinned buffers from host_buffers()) the results are left in host memory and the
-        compressed blob leaves the device in `groups` pieces while the rest is still being compressed."""
+        compressed blob leaves the device in `groups` pieces while the rest is still being compressed.
+        l4 (device results only): the similarity layer runs SHARD-LOCALLY on the chunks that are first occurrences in
+        the whole stream - `base` holds local chunk indices and bases never live on another GPU (near duplicates
+        whose original sits in another shard are stored whole); chunks that keep a delta are not compressed."""
         import torch.distributed as dist
         ctx = self.ctx
         dev = ctx.tdev
@@ -461,14 +467,22 @@ class ShardedIngest(Ingest):
         ctx.check(ctx.lib.hmse_dedup_scatter(ctx.h, reply.data_ptr(), perm.data_ptr(), n, id_base, canon.data_ptr(),
                                              first.data_ptr(), ctx.stream))
         canon, first = canon[:n], first[:n]
-        sel = self.select_first(first)
+        base = dblob = doffs = None
+        stored = first
+        if l4 is not None and n:
+            if host is not None:
+                raise ValueError("l4 is not available together with host result buffers")
+            base, dblob, doffs = self.similarity_delta(d, cuts, first.view(torch.bool), l4, min_votes, start0=entry)
+            stored = (first.view(torch.bool) & (base < 0)).view(torch.uint8)
+        sel = self.select_first(stored)
         if host is not None:
             return self._compress_to_host(d, cuts, digests, canon, first, sel, entry, id_base, host, groups)
         if compress:
             blob, offs = ctx.compress(d, cuts, sel, self.zdict, self.level, start0=entry)
         else:
             blob, offs = ctx.empty(0, torch.uint8), ctx.empty(1, torch.int64).zero_()
-        return IngestResult(cuts, digests, canon, first.view(torch.bool), sel, blob, offs, entry, id_base)
+        return IngestResult(cuts, digests, canon, first.view(torch.bool), sel, blob, offs, entry, id_base,
+                            base=base, delta_blob=dblob, delta_offsets=doffs)
 
     def run_batches(self, batches, n_own: int, eof: bool, host, groups: int = 8):
         """A sequence of shard buffers in pinned host memory (one per step of a continuous ingest): generator of

@@ -235,7 +235,8 @@ int hmse_lsh_buckets(hmse_ctx* ctx, const uint64_t* d_keys, uint64_t n, uint32_t
  *        varint = unsigned LEB128.  Chunks and bases longer than 32768 bytes are never delta-coded. ------- */
 
 /* Base selection over the sorted triples of hmse_lsh_buckets (n chunks, bands <= 32, ids id_base..id_base+n-1):
- * head(i, b) = first chunk of the bucket chunk i falls in for band b; votes(i, j) = bands whose head is j < i;
+ * head(i, b) = first chunk with d_is_first set of the bucket chunk i falls in for band b (only chunks that passed exact
+ * dedup enter the index); votes(i, j) = bands whose head is j < i;
  * root(i) = d_is_first[i] and no j reaches min_votes; d_base[i] = the root with the most votes >= min_votes
  * (ties to the smaller index) as a LOCAL index, or -1 (also for duplicates).  Bases are roots: no chains. */
 int hmse_delta_bases(hmse_ctx* ctx, const uint32_t* d_band, const uint64_t* d_key, const uint64_t* d_id, uint64_t n,

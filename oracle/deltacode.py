@@ -9,8 +9,12 @@ so - **parity unpinned** - this module defines the coding the spec's example des
 op list) completely, and the GPU build must reproduce it byte for byte:
 
 Base selection (the "probe LSH index -> return base chunk" step, README.md:1556-1559)
-    head(i, b)  = smallest chunk id j with keys[j][b] == keys[i][b]   (the entry an LSH index
-                  that keeps the first chunk of every bucket returns for the probe of band b)
+    head(i, b)  = smallest first-occurrence chunk id j with keys[j][b] == keys[i][b]   (the entry
+                  an LSH index that keeps the first chunk of every bucket returns for the probe of
+                  band b; only chunks that passed exact dedup are ever inserted, README.md:1553-1556.
+                  In one stream a duplicate has an earlier first occurrence with the same keys, so
+                  the restriction changes nothing there; it matters for a shard whose duplicates
+                  have their first occurrence in another shard)
     votes(i, j) = number of bands b with head(i, b) == j, for j < i
     root(i)     = is_first[i] and max_j votes(i, j) < min_votes       (nothing earlier is similar:
                   the chunk is stored whole and may serve as a base)
@@ -61,9 +65,13 @@ def lsh_heads(keys: np.ndarray) -> np.ndarray:
 
 def delta_bases(keys: np.ndarray, is_first: np.ndarray, min_votes: int = MIN_VOTES) -> np.ndarray:
     """base int64[n] as defined in the module docstring."""
-    heads = lsh_heads(keys)
-    n = heads.shape[0]
+    keys = np.asarray(keys, dtype=np.uint64)
+    n = keys.shape[0]
     is_first = np.asarray(is_first, dtype=bool)
+    idx = np.flatnonzero(is_first)
+    heads = np.tile(np.arange(n, dtype=np.int64)[:, None], (1, keys.shape[1]))   # duplicates: no head but themselves
+    if idx.size:
+        heads[idx] = idx[lsh_heads(keys[idx])]
     root = np.zeros(n, dtype=bool)
     votes = []
     for i in range(n):

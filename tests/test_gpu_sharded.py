@@ -45,13 +45,18 @@ for hb in pipe.run_batches([hin, hin, hin], per, eof, host=pipe.host_buffers(n_a
     assert hb.h2d_bytes == n_avail
     nb += 1
 assert nb == 3
+# shard-local L4: deltas against bases of the same shard, first-occurrence flags from the global dedup
+l4 = hmse_b200.ShardedIngest(ctx, cfg, zd).run(d, per, eof, l4=hmse_b200.SimConfig())
+assert np.array_equal(l4.cuts.cpu().numpy(), res.cuts.cpu().numpy()) and np.array_equal(l4.canon.cpu().numpy(), res.canon.cpu().numpy())
 sig, keys, (lb, lk, li) = hmse_b200.ShardedSimilarity(ctx).run(d, res.cuts, start0=res.entry)
 torch.cuda.synchronize()
 out = dict(rank=rank, cuts=(res.cuts.cpu().numpy().view(np.uint64) + np.uint64(rank * per)).tolist(),
            canon=res.canon.cpu().numpy().tolist(), first=res.is_first.cpu().numpy().astype(int).tolist(),
            digests=res.digests.cpu().numpy().tobytes().hex(), id_base=res.id_base, entry=res.entry,
            blob=res.blob.cpu().numpy().tobytes().hex(), offs=res.offsets.cpu().numpy().tolist(),
-           sel=res.select.cpu().numpy().tolist(), keys=keys.cpu().numpy().view(np.uint64).tolist(),
+           sel=res.select.cpu().numpy().tolist(), l4_base=l4.base.cpu().numpy().tolist(), l4_sel=l4.select.cpu().numpy().tolist(),
+           l4_dblob=l4.delta_blob.cpu().numpy().tobytes().hex(), l4_doffs=l4.delta_offsets.cpu().numpy().tolist(),
+           l4_nstreams=int(l4.offsets.numel() - 1), keys=keys.cpu().numpy().view(np.uint64).tolist(),
            lsh=[lb.cpu().numpy().tolist(), lk.cpu().numpy().view(np.uint64).tolist(), li.cpu().numpy().tolist()])
 json.dump(out, open(os.path.join(%r, "shard_%%d.json" %% rank), "w"))
 dist.destroy_process_group()
@@ -112,3 +117,20 @@ def test_two_gpu_sharded_ingest(tmp_path):
             g = o["id_base"] + j
             assert wf[g]
             assert streams[k] == raw[int(starts[g]):int(want_cuts[g])]
+    # shard-local L4 equals the oracle's delta() run on each shard's chunks with the global first-occurrence flags
+    pos = 0
+    n_delta = 0
+    for o in outs:
+        nloc = len(o["canon"])
+        lc = want_cuts[pos:pos + nloc]
+        s0 = int(starts[pos])
+        shard = data[s0:int(lc[-1])]
+        rel = (lc - np.uint64(s0)).astype(np.uint64)
+        keys_loc = want_keys[pos:pos + nloc]
+        wbase, wblob, woffs = oracle.delta(shard, rel, keys_loc, wf[pos:pos + nloc])
+        assert o["l4_base"] == wbase.tolist()
+        assert bytes.fromhex(o["l4_dblob"]) == wblob.tobytes() and o["l4_doffs"] == woffs.astype(np.int64).tolist()
+        assert o["l4_sel"] == np.flatnonzero(wf[pos:pos + nloc] & (wbase < 0)).tolist() and o["l4_nstreams"] == len(o["l4_sel"])
+        n_delta += int((wbase >= 0).sum())
+        pos += nloc
+    assert n_delta > 20
