@@ -37,7 +37,7 @@ constexpr int OWN_CAP = 4;        // nearest own-chunk candidates examined per p
 // Own-chunk candidates per size class.  On the 8 KiB-average corpus most matches of a short chunk come from the preset
 // dictionary: with two own candidates instead of four the small class loses 0.06 % (4 KiB chunks) to 0.2 % (8 KiB CDC
 // chunks) of size and stays at zlib-6 parity (1.0001x), while a 32 KiB chunk would lose 1.8 % - so the depth follows
-// the class (CPU model, tests/model: own/dict 4/4, 3/4, 2/4 -> 0.9978 / 0.9985 / 1.0001 x zlib-6 on CDC chunks;
+// the class (CPU size model of the test suite: own/dict 4/4, 3/4, 2/4 -> 0.9978 / 0.9985 / 1.0001 x zlib-6 on CDC chunks;
 // 0.9982 / 0.9994 / 1.0020 on 16 KiB; 1.0051 / 1.0115 / 1.0231 on 32 KiB).
 constexpr int OWN_SMALL = 2, OWN_MEDIUM = 3, OWN_LARGE = 4;
 constexpr int DICT_CAP = 4;       // nearest dictionary candidates examined per position (one 16-byte bucket record)
