@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     StA r;
                     r.sig = 0; r.bk = make_uint4(0, 0, 0, 0);
                     const int i = (int)(WIN * w) - OWN + (int)lane;
-                    if (w < nwin && i >= 0 && i < (int)nh) {
+                    // (a window past the last one only reads in-range context elements that nobody consumes)
+                    if ((uint32_t)i < nh) {
                         const uint32_t p = s_sorted[i];
                         // bytes p-1 .. p+3 lie in two consecutive words: one pair of loads serves both the value and
                         // the byte before it
@@ -593,13 +594,11 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                             if ((mask >> sl) & 1u) plist[o++] = rec[sl];
                         pcnt += __shfl_sync(0xffffffffu, inc, 31);
                         __syncwarp();
-                        const long long tb0 = clock64();
                         while (pcnt >= 32) {
                             pcnt -= 32;
                             extend_pairs(pcnt, 32);
                         }
                         __syncwarp();
-                        if (t == 0) atomicAdd(&g_prof[10], (unsigned long long)(clock64() - tb0));
                     }
                 }
                 if (pcnt) extend_pairs(0, pcnt);

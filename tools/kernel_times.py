@@ -68,8 +68,8 @@ def main():
         ctx.lib.hmse_debug_deflate_prof(prof, 1)
         tot = sum(prof[i] for i in range(12))
         names = ["P0 stage", "adler", "P1-2 hist+scan", "P3 scatter", "P3b bucket sort", "P4 match", "P5 dp", "P6 hop",
-                 "P7 hist+tokens", "P4c runs->match", "(P4 phase B, warp 0)", "-"]
-        res["parse_phase_pct"] = {names[i]: round(100.0 * prof[i] / max(1, tot), 1) for i in range(11)}
+                 "P7 hist+tokens", "P4c runs->match", "-", "-"]
+        res["parse_phase_pct"] = {names[i]: round(100.0 * prof[i] / max(1, tot), 1) for i in range(10)}
         res["parse_cycles_per_chunk"] = tot / max(1, prof[15])
         ms, (blob, offs) = timed(lambda: ctx.compress(d, cuts, sel, zd), reps=3)
         res["deflate_ms"], res["deflate_GBps"], res["deflate_ratio"] = ms, ub / ms / 1e6, ub / max(1, blob.numel())
