@@ -78,7 +78,8 @@ constexpr int SHA_THREADS = 128;
 template <int FMA_ADDS>
 __global__ void __launch_bounds__(SHA_THREADS)
 sha256_kernel(const uint8_t* __restrict__ data, uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t n_chunks,
-              uint8_t* __restrict__ digests, unsigned long long* __restrict__ counter, uint32_t one) {
+              uint8_t* __restrict__ digests, unsigned long long* __restrict__ counter, uint32_t one,
+              const uint32_t* __restrict__ order) {
     uint32_t H[8], W[16];
     uint64_t j = 0, s = 0, len = 0, blk = 0, nblk = 0;
     bool have = false, done = false;
@@ -88,6 +89,7 @@ sha256_kernel(const uint8_t* __restrict__ data, uint64_t start0, const uint64_t*
             if (j >= n_chunks) {
                 done = true;
             } else {
+                if (order) j = order[j];   // longest chunks first when the lanes get only a few chunks each
                 s = j ? cuts[j - 1] : start0;
                 len = cuts[j] - s;
                 nblk = (len + 9 + 63) >> 6;
@@ -147,6 +149,44 @@ sha256_kernel(const uint8_t* __restrict__ data, uint64_t start0, const uint64_t*
     }
 }
 
+// Longest-first work order for batches that give every lane only a few chunks (a piece of a stream): chunk indices
+// grouped by length class (2 KiB steps), longest class first, so the lanes that finish last hold short chunks.  The
+// order inside a class is whatever the atomics give - the digests do not depend on it.
+constexpr int LEN_CLASSES = 33;
+__device__ __forceinline__ uint32_t len_class(uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t j) {
+    const uint64_t len = cuts[j] - (j ? cuts[j - 1] : start0);
+    return len >> 11 < LEN_CLASSES - 1 ? (uint32_t)(len >> 11) : LEN_CLASSES - 1;
+}
+// (one atomic per class and warp: the lanes of a class are counted with a match)
+__global__ void sha_class_hist_kernel(uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t n, uint32_t* __restrict__ hist) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = j < n ? len_class(start0, cuts, j) : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, c);
+    if (j < n && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[c], (uint32_t)__popc(peers));
+}
+__global__ void sha_class_scan_kernel(uint32_t* __restrict__ hist) {   // cursor[c] = chunks in longer classes
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int c = LEN_CLASSES - 1; c >= 0; c--) {
+            const uint32_t k = hist[c];
+            hist[c] = run;
+            run += k;
+        }
+    }
+}
+__global__ void sha_class_scatter_kernel(uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t n, uint32_t* __restrict__ cursor,
+                                         uint32_t* __restrict__ order) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t c = j < n ? len_class(start0, cuts, j) : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (j < n && lane == (uint32_t)leader) base = atomicAdd(&cursor[c], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (j < n) order[base + __popc(peers & ((1u << lane) - 1))] = (uint32_t)j;
+}
+
 }  // namespace
 
 HMSE_API int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
@@ -157,17 +197,32 @@ HMSE_API int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, 
     if (!d_data || !d_cuts || !d_digests) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_digest: null pointer");
     if ((uintptr_t)d_digests & 15) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_digests must be 16-byte aligned");
     if ((uintptr_t)d_data & 3) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_data must be 4-byte aligned");
-    HMSE_SCRATCH(ctx, counter, unsigned long long*, SLOT_SHA_MISC, 64);
-    HMSE_CUDA(ctx, cudaMemsetAsync(counter, 0, 8, st));
+    if (n_chunks > 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_digest: n_chunks exceeds 2^32");
     // persistent lanes: enough warps to fill the machine, never more lanes than chunks
     uint64_t blocks = div_up64(n_chunks, SHA_THREADS);
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
     if (blocks > max_blocks) blocks = max_blocks;
+    const uint64_t lanes = max_blocks * SHA_THREADS;
+    // between one and six chunks per lane the stream order leaves long chunks for the end: order them longest first
+    const bool lpt = n_chunks > lanes && n_chunks < 6 * lanes;
+    // misc: [counter u64][class counters u32 x 64][order u32 n]
+    HMSE_SCRATCH(ctx, counter, unsigned long long*, SLOT_SHA_MISC, 8 + 256 + (lpt ? n_chunks * 4 : 0) + 64);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(counter + 1);
+    uint32_t* order = lpt ? hist + 64 : nullptr;
+    HMSE_CUDA(ctx, cudaMemsetAsync(counter, 0, 8 + 256, st));
     HT_BEGIN(ctx, HT_SHA, st);
+    if (lpt) {
+        KL(ctx);
+        sha_class_hist_kernel<<<(unsigned)div_up64(n_chunks, 256), 256, 0, st>>>(start0, d_cuts, n_chunks, hist);
+        KL(ctx);
+        sha_class_scan_kernel<<<1, 32, 0, st>>>(hist);
+        KL(ctx);
+        sha_class_scatter_kernel<<<(unsigned)div_up64(n_chunks, 256), 256, 0, st>>>(start0, d_cuts, n_chunks, hist, order);
+    }
     KL(ctx);
     // FMA_ADDS = 2 (message schedule and round additions as IMADs) measured on B200: 14.6 -> 13.1 ms per 10 GB
     // (687 -> 763 GB/s); moving the W + K addition as well (a second IMAD) was slower again (13.5 ms).
-    sha256_kernel<2><<<(unsigned)blocks, SHA_THREADS, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_digests, counter, 1u);
+    sha256_kernel<2><<<(unsigned)blocks, SHA_THREADS, 0, st>>>(d_data, start0, d_cuts, n_chunks, d_digests, counter, 1u, order);
     HMSE_LAUNCH_CHECK(ctx);
     HT_END(ctx, HT_SHA, st);
     return HMSE_OK;
