@@ -730,7 +730,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 }
             }
             uint32_t w_off = block_excl_scan(words, sm->warp_tmp, &n_words);
-            uint16_t* tk = a.tokens + (size_t)bj * nmax;
+            // the token words are gathered in shared memory (the exit table is dead after P6) and leave as 16-byte
+            // vectors: written where they are produced, every 2-byte store of a warp would touch its own 32-byte sector
+            uint16_t* s_tok = s_exit;   // n_words <= n
             for (uint32_t r = r0; r < r1; r++) {
                 const uint32_t e = s_entry[r];
                 if (e == 0xFF) continue;
@@ -738,16 +740,21 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 for (uint32_t p = (r << RS) + e; p < pe;) {
                     const uint32_t mw = mptr[SK(p)];
                     if (mw_is_match(mw)) {
-                        tk[w_off++] = (uint16_t)(0x8000u | (mw >> 16));
-                        tk[w_off++] = (uint16_t)(mw & 0x7fffu);
+                        s_tok[w_off++] = (uint16_t)(0x8000u | (mw >> 16));
+                        s_tok[w_off++] = (uint16_t)(mw & 0x7fffu);
                         p += mw >> 16;
                     } else {
-                        tk[w_off++] = s_data[p];
+                        s_tok[w_off++] = s_data[p];
                         p += 1;
                     }
                 }
             }
             __syncthreads();
+            {
+                uint4* tk4 = reinterpret_cast<uint4*>(a.tokens + (size_t)bj * nmax);   // nmax is a multiple of 8 words
+                const uint4* st4 = reinterpret_cast<const uint4*>(s_tok);
+                for (uint32_t i = t; i < (n_words + 7) / 8; i += T) tk4[i] = st4[i];   // (the last vector may carry stale words)
+            }
             for (uint32_t i = t; i < REC_WORDS; i += T)
                 a.hist[(size_t)bj * REC_WORDS + i] = sm->hist[i] + (i == (uint32_t)EOB ? 1u : 0u);
         }
