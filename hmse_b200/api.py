@@ -241,7 +241,9 @@ class Context:
         n = cuts.numel()
         offsets = self.empty(n + 1, torch.int64)
         total = C.c_uint64(0)
-        out_cap = 1 << 20
+        # kept deltas are a fraction of a percent of the stream (0.14 % on the wiki corpus): 1/64 of it rarely needs the
+        # retry, which repeats the whole encode
+        out_cap = max(1 << 20, int(d.numel()) // 64)
         for _ in range(2):
             out = self.empty(out_cap + _PAD, torch.uint8)
             rc = self.lib.hmse_delta_encode(self.h, d.data_ptr(), start0, cuts.data_ptr(), n, base.data_ptr(),
