@@ -324,3 +324,35 @@ def test_delta_api_errors(ctx):
     with pytest.raises(hmse_b200.HmseError):
         ctx.delta_bases(band, key, ids, n, 32, ones, 0)          # min_votes 0
     assert ctx.delta_bases(band, key, ids, n, 32, ones, 4).cpu().tolist() == [-1] * n
+
+
+def test_delta_encode_capacity_protocol(ctx):
+    """Too small an output buffer: HMSE_E_CAPACITY with the required size, the candidate list untouched; a second call
+    with that size succeeds and gives the oracle's bytes."""
+    import ctypes as C
+    import torch
+    from hmse_b200 import _lib
+    rng = np.random.default_rng(21)
+    pairs = []
+    for _ in range(8):
+        b = bytes(rng.integers(97, 123, 6000, dtype=np.uint8))
+        t = bytearray(b)
+        t[3000:3000] = b"0123456789" * 5
+        pairs.append((b, bytes(t)))
+    data, cuts, base = _pairs_to_stream(pairs)
+    dd, ct = ctx.stage(data), _t64(cuts)
+    bt = torch.from_numpy(base.copy()).cuda()
+    n = cuts.size
+    offs = ctx.empty(n + 1, torch.int64)
+    total = C.c_uint64(0)
+    small = ctx.empty(64, torch.uint8)
+    rc = ctx.lib.hmse_delta_encode(ctx.h, dd.data_ptr(), 0, ct.data_ptr(), n, bt.data_ptr(), small.data_ptr(), 16,
+                                   offs.data_ptr(), C.byref(total), ctx.stream)
+    assert rc == _lib.HMSE_E_CAPACITY and total.value > 16
+    want = [D.delta_encode(t, b) for b, t in pairs]
+    assert total.value == sum(len(w) for w in want)
+    assert np.array_equal(bt.cpu().numpy(), base)          # still the candidates: nothing was rejected
+    out = ctx.empty(int(total.value) + 64, torch.uint8)
+    ctx.check(ctx.lib.hmse_delta_encode(ctx.h, dd.data_ptr(), 0, ct.data_ptr(), n, bt.data_ptr(), out.data_ptr(), int(total.value),
+                                        offs.data_ptr(), C.byref(total), ctx.stream))
+    assert out[:total.value].cpu().numpy().tobytes() == b"".join(want)
