@@ -314,18 +314,19 @@ def run_ours(args):
     parse_gbs = alg_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
     defl_bytes = sel_bytes + out_bytes
     defl_gbs = defl_bytes / (stage_ms["deflate"] * 1e-3) / 1e9 if stage_ms["deflate"] > 0 else 0.0
-    traffic = traffic_note = None
+    traffic = traffic_note = ncu_facts = None
     try:
         with open(os.path.join(ROOT, "profiles", "deflate_traffic.json")) as f:
             tj = json.load(f)
             traffic = tj.get("dram_bytes_per_launch")
             traffic_note = tj.get("note")
+            ncu_facts = tj.get("ncu")
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "kernel": "parse_kernel (match search + parse of one batch of chunks; the other kernels of "
                                           "the stage are listed under other_kernels)",
                 "achieved": parse_gbs, "peak": peak, "unit": "GB/s", "frac": parse_gbs / peak, "traffic": traffic,
-                "traffic_note": traffic_note, "peak_source": peak_src,
+                "traffic_note": traffic_note, "ncu": ncu_facts, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_per_launch, "ms_per_launch": ms_per_launch,
                 "launches_per_step": parse["launches"] / max(1, args.steps), "launches_timed": parse["timed"],
                 "other_kernels": {k: {"ms": stage_ms[k],
