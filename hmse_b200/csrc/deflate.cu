@@ -46,8 +46,8 @@ constexpr uint32_t DICT_BUCKETS = 1u << DICT_HASH_BITS;
 constexpr uint32_t DICT_MAX = 32768;
 // Size classes of parse_kernel (bytes per chunk): the small class keeps its match words in shared memory, the medium
 // and large ones in global scratch; small and medium fit two CTAs per SM, large one.  On the 8 KiB-average corpus
-// 83 % of the bytes are small, 17 % medium (12-20 KiB), < 0.5 % large.
-constexpr uint32_t NMAX_SMALL = 12288, NMAX_MEDIUM = 20480, NMAX_LARGE = 32768;
+// 87 % of the bytes are small (<= 13 KiB: the most that lets two CTAs share an SM), 12.5 % medium (13-20 KiB), < 0.5 % large.
+constexpr uint32_t NMAX_SMALL = 13312, NMAX_MEDIUM = 20480, NMAX_LARGE = 32768;
 constexpr int N_CLASS = 3, LONG_CLASS = 3;   // class 3: longer than NMAX_LARGE (multi-block streams)
 static_assert(NMAX_LARGE / 512 <= 64, "P3b keeps one moved-bit per element of a thread");
 constexpr int T_PARSE = 512;

@@ -153,7 +153,7 @@ def test_constant_chunks(ctx, fill):
 def test_tiny_and_ragged_chunks(ctx, corpus8):
     import hmse_b200
     lens = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 257, 258, 259, 260, 1000,
-                     4095, 4096, 4097, 12287, 12288, 12289, 32767, 32768, 32769, 40000])
+                     4095, 4096, 4097, 12287, 12288, 12289, 13311, 13312, 13313, 20479, 20480, 20481, 32767, 32768, 32769, 40000])
     cuts = np.cumsum(lens).astype(np.uint64)
     d = corpus8[3:3 + int(cuts[-1])]
     zd = corpus.zdict()

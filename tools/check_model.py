@@ -32,7 +32,7 @@ def main():
     tot_g = tot_m = 0
     for k, (s, e) in enumerate(zip(starts.tolist(), np.asarray(cuts).astype(np.int64).tolist())):
         ch = np.ascontiguousarray(data[s:e])
-        pr = prs[2 if e - s <= 12288 else 3 if e - s <= 20480 else 4]
+        pr = prs[2 if e - s <= 13312 else 3 if e - s <= 20480 else 4]
         r = lib.model_compress(ch.ctypes.data, e - s, zdn.ctypes.data, len(zd), C.byref(pr), out.ctypes.data, out.size, st)
         tot_g += int(sizes[k]); tot_m += int(r)
         if r != sizes[k]:
