@@ -71,3 +71,22 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "tests/model" not in src or f == "deflate_core.h", f
+
+
+def test_stream_piece_schedule_covers_the_stream():
+    """IngestStream.schedule (host logic, no GPU): piece ends are increasing, 16-byte aligned except the last, end at n,
+    with and without the ramp at the start (a prefetched stream needs none)."""
+    from hmse_b200 import ingest, CDCConfig
+    st = ingest.IngestStream.__new__(ingest.IngestStream)
+    st.cdc = CDCConfig()
+    for piece in (1 << 20, 64 << 20, 1 << 30, 2 << 30):
+        st.piece = piece
+        for n in (1, 4095, 5_000_000, (3 << 30) + 12345, 10_000_000_000):
+            for ramp in (True, False):
+                ends = st.schedule(n, ramp)
+                assert ends[-1] == n and all(b > a for a, b in zip(ends, ends[1:])) and ends[0] > 0
+                assert all(e % 16 == 0 for e in ends[:-1]), (piece, n, ramp)
+                sizes = [ends[0]] + [b - a for a, b in zip(ends, ends[1:])]
+                assert max(sizes) <= max(piece, 16) + 16 or len(ends) == 1 or n <= 2 * piece, (piece, n, ramp, sizes[:4])
+            if n > 4 * piece:
+                assert st.schedule(n, False)[0] == piece and st.schedule(n, True)[0] < piece
