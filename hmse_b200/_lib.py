@@ -8,8 +8,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhmse_b200.so")
 
-HMSE_OK, HMSE_E_INVAL, HMSE_E_CAPACITY, HMSE_E_CUDA, HMSE_E_NOMEM = 0, -1, -2, -3, -4
-ABI_VERSION = 1
+HMSE_OK, HMSE_E_INVAL, HMSE_E_CAPACITY, HMSE_E_CUDA, HMSE_E_NOMEM, HMSE_E_NCCL = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 2
 
 
 class HmseError(RuntimeError):
@@ -68,7 +68,16 @@ SIGNATURES = {
     "hmse_lsh_buckets": (_I, [_P, _P, _U64, _U32, _U64, _P, _P, _P, _P]),
     "hmse_delta_bases": (_I, [_P, _P, _P, _P, _U64, _U32, _U64, _P, _U32, _P, _P]),
     "hmse_delta_encode": (_I, [_P, _P, _U64, _P, _U64, _P, _P, _U64, _P, _PU64, _P]),
-    "hmse_delta_apply": (_I, [_P, _P, _P, _U64, _P, _P, _P, _P, _P, _P, _PU64, _P]),
+    "hmse_delta_apply": (_I, [_P, _P, _P, _U64, _P, _U64, _P, _P, _P, _P, _P, _PU64, _P]),
+    "hmse_comm_unique_id": (_I, [_P]),
+    "hmse_comm_init": (_I, [_P, _P, _I, _I]),
+    "hmse_comm_destroy": (_I, [_P]),
+    "hmse_comm_info": (_I, [_P, _P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "hmse_allgather_u64": (_I, [_P, _P, _PU64, _PU64, _P]),
+    "hmse_chunk_sharded": (_I, [_P, _P, _P, _U64, _U64, _I, C.POINTER(CdcCfg), _P, _U64, _PU64, _PU64, _PU64, _PU64, _P]),
+    "hmse_dedup_global": (_I, [_P, _P, _P, _U64, _U64, _P, _P, _P]),
+    "hmse_lsh_exchange": (_I, [_P, _P, _P, _U64, _U32, _P, _U64, _PU64, _PU64, C.POINTER(_U32), _P]),
+    "hmse_exchange_stats": (_I, [_P, _PU64, C.POINTER(_I)]),
     "hmse_corpus_lengths": (_I, [_P, C.POINTER(CorpusCfg), _P, _U64, _U64, _P, _P]),
     "hmse_corpus_render": (_I, [_P, C.POINTER(CorpusCfg), _P, _P, _U64, _U64, _P, _U64, _U64, _P, _P]),
 }

@@ -47,6 +47,7 @@ class Context:
             raise HmseError(rc, "hmse_create failed")
         self.h = h
         self._cdc_cache = {}
+        self.comm_world = self.comm_rank = 0   # set by comm_init: this ctx owns an NCCL communicator
 
     def close(self):
         if getattr(self, "h", None):
@@ -87,7 +88,10 @@ class Context:
             if data.dtype != torch.uint8 or not data.is_cuda:
                 raise TypeError("device input must be a CUDA uint8 tensor")
             data = data.contiguous().view(-1)
-            if data.data_ptr() % 16 == 0:
+            # kernels read whole 16-byte vectors: besides the alignment, _PAD bytes of the same allocation must follow the
+            # data (a tensor that ends exactly at the end of its storage could end at the end of a cudaMalloc segment)
+            slack = data.untyped_storage().nbytes() - data.storage_offset() - data.numel()
+            if data.data_ptr() % 16 == 0 and slack >= _PAD:
                 return data
             buf = self.empty(data.numel() + _PAD, torch.uint8)
             buf[:data.numel()].copy_(data)
@@ -139,6 +143,72 @@ class Context:
         self.check(self.lib.hmse_chunk_resolve(self.h, d.data_ptr(), n_own, n, int(eof), entry, cuts.data_ptr(), cap,
                                                C.byref(nc), C.byref(ex), self.stream))
         return cuts[:nc.value], ex.value
+
+    # -- multi-GPU: the exchange steps behind the C ABI (csrc/comm.cu, NCCL) ------------------------
+    def comm_init(self, group=None) -> None:
+        """Creates this context's NCCL communicator over the ranks of a torch.distributed group (default: the world
+        group): rank 0 draws the ncclUniqueId, torch.distributed carries its 128 bytes, every rank calls hmse_comm_init.
+        torch.distributed is only the side channel here - the data path collectives are issued by the library."""
+        import torch.distributed as dist
+        if self.comm_world:
+            return
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            rc = self.lib.hmse_comm_unique_id(buf)
+            if rc != 0:
+                raise HmseError(rc, "hmse_comm_unique_id failed (is libnccl.so.2 loadable?)")
+            uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = uid.to(self.tdev) if on_gpu else uid
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self.check(self.lib.hmse_comm_init(self.h, raw, world, rank))
+        self.comm_world, self.comm_rank = world, rank
+
+    def chunk_sharded(self, d: torch.Tensor, cfg: CDCConfig, n_own: int, eof: bool):
+        """(cuts, entry, id_base, n_total) of this rank's byte-range shard of one stream (hmse_chunk_sharded)."""
+        n = d.numel()
+        own = n if eof else n_own
+        cap = own // cfg.min_size + 2
+        cuts = self.empty(cap, torch.int64)
+        nc, en, ib, nt = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.hmse_chunk_sharded(self.h, None, d.data_ptr(), n_own, n, int(eof), C.byref(self.cdc_struct(cfg)),
+                                               cuts.data_ptr(), cap, C.byref(nc), C.byref(en), C.byref(ib), C.byref(nt),
+                                               self.stream))
+        return cuts[:nc.value], en.value, ib.value, nt.value
+
+    def dedup_global(self, digests: torch.Tensor, id_base: int):
+        """(canon int64[n] of GLOBAL ids, is_first uint8[n]) over every rank's digests (hmse_dedup_global)."""
+        n = digests.shape[0]
+        canon = self.empty(max(n, 1), torch.int64)
+        first = self.empty(max(n, 1), torch.uint8)
+        self.check(self.lib.hmse_dedup_global(self.h, None, digests.data_ptr(), n, id_base, canon.data_ptr(), first.data_ptr(),
+                                              self.stream))
+        return canon[:n], first[:n]
+
+    def lsh_exchange(self, keys: torch.Tensor):
+        """(owned int64 [N_total, bands_owned], id_base): the owned bands' keys of every chunk of the stream."""
+        n, bands = int(keys.shape[0]), int(keys.shape[1])
+        nt, ib, bo = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        keys = keys.contiguous()
+        self.check(self.lib.hmse_lsh_exchange(self.h, None, keys.data_ptr(), n, bands, None, 0, C.byref(nt), C.byref(ib),
+                                              C.byref(bo), self.stream))
+        owned = self.empty(max(1, nt.value * bo.value), torch.int64)
+        self.check(self.lib.hmse_lsh_exchange(self.h, None, keys.data_ptr(), n, bands, owned.data_ptr(), nt.value, C.byref(nt),
+                                              C.byref(ib), C.byref(bo), self.stream))
+        return owned[:nt.value * bo.value].view(nt.value, bo.value), ib.value
+
+    def exchange_stats(self):
+        """{bytes_sent, bytes_received, owned, contributed, rounds, ms} of the last exchange (ms only with hmse_timing on)."""
+        out = (C.c_uint64 * 4)()
+        rounds = C.c_int(0)
+        self.check(self.lib.hmse_exchange_stats(self.h, out, C.byref(rounds)))
+        f = C.c_float(0)
+        ms = f.value if self.lib.hmse_timing_ms(self.h, 10, C.byref(f)) == 0 else None
+        return {"bytes_sent": int(out[0]), "bytes_received": int(out[1]), "owned": int(out[2]), "contributed": int(out[3]),
+                "rounds": int(rounds.value), "ms": ms}
 
     # -- L3 -------------------------------------------------------------------------------
     def digest(self, d: torch.Tensor, cuts: torch.Tensor, start0: int = 0) -> torch.Tensor:
@@ -264,7 +334,7 @@ class Context:
         status = self.empty(max(m, 1), torch.int32)[:m]
         bad = C.c_uint64(0)
         self.check(self.lib.hmse_delta_apply(self.h, blob.data_ptr(), offsets.data_ptr(), m, base_data.data_ptr(),
-                                             base_off.data_ptr(), base_len.data_ptr(), out.data_ptr(), out_offsets.data_ptr(),
+                                             base_data.numel(), base_off.data_ptr(), base_len.data_ptr(), out.data_ptr(), out_offsets.data_ptr(),
                                              status.data_ptr(), C.byref(bad), self.stream))
         return out, status, int(bad.value)
 

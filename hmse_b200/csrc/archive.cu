@@ -11,9 +11,12 @@
 
 namespace {
 
-__global__ void slot_of_kernel(const uint64_t* __restrict__ select, uint64_t m, uint32_t* __restrict__ slot_of) {
+__global__ void slot_of_kernel(const uint64_t* __restrict__ select, uint64_t m, uint64_t n, uint32_t* __restrict__ slot_of,
+                               unsigned int* __restrict__ err) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < m) slot_of[select[k]] = (uint32_t)k;
+    if (k >= m) return;
+    if (select[k] < n) slot_of[select[k]] = (uint32_t)k;
+    else atomicOr(err, 16u);
 }
 
 __global__ void pointer_kernel(const int64_t* __restrict__ canon, uint64_t id_base, const uint64_t* __restrict__ cuts,
@@ -22,7 +25,15 @@ __global__ void pointer_kernel(const int64_t* __restrict__ canon, uint64_t id_ba
                                uint2* __restrict__ pointers, unsigned int* __restrict__ err) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t s = slot_of[(uint64_t)canon[i] - id_base];
+    // canon is a global id: a chunk whose first occurrence lies in another shard (canon < id_base or >= id_base + n) has no
+    // record in this shard's store - reported, never dereferenced
+    const uint64_t c = (uint64_t)canon[i] - id_base;
+    const uint32_t s = c < n ? slot_of[c] : 0xFFFFFFFFu;
+    if (s == 0xFFFFFFFFu) {
+        atomicOr(err, 4u);
+        pointers[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        return;
+    }
     atomicAdd(&refcount[s], 1u);
     const uint64_t pos = offsets[s];
     const uint64_t raw = cuts[i] - (i ? cuts[i - 1] : start0);
@@ -88,6 +99,7 @@ __global__ void pointer_l4_kernel(const int64_t* __restrict__ canon, const uint6
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t c = (uint64_t)canon[i];
+    if (c >= n) { atomicOr(err, 4u); pointers[i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); return; }
     uint64_t pos;
     if (delta_off[c + 1] > delta_off[c]) {
         pos = store_bytes + 8 * rank[c] + delta_off[c];
@@ -173,7 +185,7 @@ HMSE_API int hmse_index_build_l4(hmse_ctx* ctx, const uint8_t* d_digests, const 
     if (n_delta && (!d_delta || !d_delta_store)) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build_l4: null delta buffers");
     if (m) {
         KL(ctx);
-        slot_of_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(d_select, m, slot_of);
+        slot_of_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(d_select, m, n, slot_of, err);
     }
     KL(ctx);
     pointer_l4_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(d_canon, d_cuts, start0, n, slot_of, d_offsets, d_base, d_delta_off,
@@ -196,6 +208,7 @@ HMSE_API int hmse_index_build_l4(hmse_ctx* ctx, const uint8_t* d_digests, const 
     if (e & 2) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build_l4: a compressed chunk is longer than 65535 bytes");
     if (e & 4) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build_l4: a chunk resolves to a chunk that is neither stored nor a delta, or a delta's base is not stored");
     if (e & 8) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build_l4: a delta is longer than 65535 bytes or its base longer than 65536");
+    if (e & 16) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build_l4: d_select holds an index >= n");
     return HMSE_OK;
 }
 
@@ -215,9 +228,10 @@ HMSE_API int hmse_index_build(hmse_ctx* ctx, const uint8_t* d_digests, const int
     uint32_t* slot_of = misc;
     uint32_t* refcount = misc + n;
     unsigned int* err = refcount + m;
+    HMSE_CUDA(ctx, cudaMemsetAsync(slot_of, 0xFF, n * 4, st));
     HMSE_CUDA(ctx, cudaMemsetAsync(refcount, 0, (m + 1) * 4, st));
     KL(ctx);
-    slot_of_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(d_select, m, slot_of);
+    slot_of_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(d_select, m, n, slot_of, err);
     KL(ctx);
     pointer_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(d_canon, id_base, d_cuts, start0, n, slot_of, d_offsets, refcount,
                                                                reinterpret_cast<uint2*>(d_pointers), err);
@@ -229,6 +243,10 @@ HMSE_API int hmse_index_build(hmse_ctx* ctx, const uint8_t* d_digests, const int
     const uint32_t e = (uint32_t)ctx->pinned[0];
     if (e & 1) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build: a chunk is empty or longer than 65536 bytes, or the store exceeds 2 TiB");
     if (e & 2) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build: a compressed chunk is longer than 65535 bytes");
+    if (e & 4)
+        HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build: a chunk resolves (canon) to a chunk outside [id_base, id_base + n) or to one "
+                                     "that is not in d_select - cross-shard duplicates have no record in a per-shard archive");
+    if (e & 16) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_index_build: d_select holds an index >= n");
     return HMSE_OK;
 }
 

@@ -23,7 +23,7 @@ HMSE_API int hmse_create(int device, hmse_ctx** out) {
         return HMSE_E_CUDA;
     }
     c->sm_count = prop.multiProcessorCount;
-    if (cudaHostAlloc((void**)&c->pinned, 4096, cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&c->pinned, HMSE_MAILBOX_BYTES, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&c->pinned_dev, c->pinned, 0) != cudaSuccess) {
         delete c;
         return HMSE_E_CUDA;
@@ -45,6 +45,7 @@ HMSE_API int hmse_create(int device, hmse_ctx** out) {
 HMSE_API void hmse_destroy(hmse_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    hmse_comm_destroy(ctx);
     for (int i = 0; i < SLOT_COUNT; i++)
         if (ctx->slot[i]) cudaFree(ctx->slot[i]);
     for (int i = 0; i < 2 * HT_COUNT; i++)
@@ -100,7 +101,7 @@ __global__ void mail_kernel(uint32_t* __restrict__ dst, const uint32_t* __restri
 }  // namespace
 
 int hmse_mail(hmse_ctx* ctx, uint32_t word32, const void* d_src, uint32_t n32, cudaStream_t stream) {
-    if ((size_t)(word32 + n32) * 4 > 4096) HMSE_FAIL(ctx, HMSE_E_INVAL, "mailbox overflow");
+    if ((size_t)(word32 + n32) * 4 > HMSE_MAILBOX_BYTES) HMSE_FAIL(ctx, HMSE_E_INVAL, "mailbox overflow");
     KL(ctx);
     mail_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t*>(ctx->pinned_dev) + word32,
                                       reinterpret_cast<const uint32_t*>(d_src), n32);

@@ -18,6 +18,7 @@ enum HmseSlot {
     SLOT_SHA_MISC,      // work counter
     SLOT_DEDUP_TABLE,   // open-addressing table of chunk indices
     SLOT_DEDUP_MISC,    // owner histogram / offsets for the partition step
+    SLOT_DEDUP_OWNER,   // owner-side table + minimum gids of the sharded exchange (never the streaming table)
     SLOT_DEFLATE_STAGE, // per-chunk worst-case output slots
     SLOT_DEFLATE_MISC,  // sizes, slot offsets, class lists, counters
     SLOT_DEFLATE_DICT,  // hash-sorted index of the preset dictionary
@@ -34,13 +35,18 @@ enum HmseSlot {
     SLOT_DELTA_STAGE,   // per-candidate worst-case (len / 5) output slots
     SLOT_DELTA_BAD,     // error count of the decoder
     SLOT_CORPUS,
+    SLOT_COMM_SMALL,    // counts / exits travelling through the all-gathers
+    SLOT_COMM_SEND,     // records (dedup) or key columns (LSH) grouped by destination rank
+    SLOT_COMM_RECV,     // what arrives, the owner's answers, the replies
     SLOT_COUNT
 };
 
 // Timed regions (hmse_timing_ms ids; also in include/hmse.h)
 constexpr int HMSE_PARSE_EVENTS = 128;
+constexpr int HMSE_MAX_WORLD = 32;          // ranks per communicator (the counts matrix must fit the mailbox)
+constexpr size_t HMSE_MAILBOX_BYTES = 16384;
 enum HmseTimer {
-    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_INFLATE, HT_DELTA, HT_COUNT
+    HT_SCAN = 0, HT_RESOLVE, HT_SHA, HT_DEDUP, HT_DEFLATE, HT_PACK, HT_MINHASH, HT_LSH, HT_INFLATE, HT_DELTA, HT_EXCHANGE, HT_COUNT
 };
 
 struct hmse_ctx {
@@ -52,7 +58,7 @@ struct hmse_ctx {
     char err[512];
     void* slot[SLOT_COUNT];
     size_t slot_bytes[SLOT_COUNT];
-    uint64_t* pinned;  // small pinned host mailbox (4 KiB), mapped: kernels write results into it directly
+    uint64_t* pinned;  // small pinned host mailbox (HMSE_MAILBOX_BYTES), mapped: kernels write results into it directly
     uint64_t* pinned_dev;  // its device-side address
     int sm_count;
     // CDC state carried from scan to resolve
@@ -71,6 +77,11 @@ struct hmse_ctx {
     uint64_t stat[4];  // [0] parse launches, [1] token words written, [2] input bytes parsed, [3] chunks parsed
     uint64_t dedup_cap, dedup_n;  // streaming dedup table (hmse_dedup_begin / hmse_dedup_append)
     void* dict_host;  // host copy + checksum of the indexed preset dictionary (deflate.cu)
+    // multi-GPU (comm.cu)
+    void* comm;       // ncclComm_t made by hmse_comm_init (null: callers pass their own)
+    int comm_owned;
+    int comm_rounds;  // stitch rounds of the last hmse_chunk_sharded
+    uint64_t comm_stat[4];  // last exchange: bytes sent to / received from other ranks, records owned, records sent
 };
 
 #define HMSE_FAIL(ctx, code, ...)                              \
@@ -118,5 +129,9 @@ int hmse_exclusive_scan_u64(hmse_ctx* ctx, const uint64_t* d_in, uint64_t* d_out
 // (the compressed blobs of the previous piece, when the caller streams), a store from an SM does not.
 // Copies n32 32-bit words from d_src to mailbox word `word32` (4-byte units).  Asynchronous on `stream`.
 int hmse_mail(hmse_ctx* ctx, uint32_t word32, const void* d_src, uint32_t n32, cudaStream_t stream);
+
+// hmse_dedup_partition without the host round trip: d_counts[world] (device) receives the records per owner.
+int hmse_dedup_partition_dev(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, uint64_t id_base, uint32_t world,
+                             uint8_t* d_records, uint32_t* d_perm, uint64_t* d_counts, cudaStream_t stream);
 
 static inline uint64_t div_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

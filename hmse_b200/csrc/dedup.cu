@@ -270,6 +270,30 @@ HMSE_API int hmse_dedup_append(hmse_ctx* ctx, const uint8_t* d_digests_all, uint
     return HMSE_OK;
 }
 
+int hmse_dedup_partition_dev(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, uint64_t id_base, uint32_t world,
+                             uint8_t* d_records, uint32_t* d_perm, uint64_t* d_counts, cudaStream_t st) {
+    if (world == 0 || world > 512) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_partition: bad world");
+    if (n > 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_partition: n exceeds 2^32");
+    // misc: [hist world][offs world][cursor world]
+    HMSE_SCRATCH(ctx, misc, uint64_t*, SLOT_DEDUP_MISC, 3 * (size_t)world * 8);
+    HMSE_CUDA(ctx, cudaMemsetAsync(misc, 0, 3 * (size_t)world * 8, st));
+    if (n) {
+        if (!d_digests || !d_records || !d_perm) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_partition: null pointer");
+        const unsigned grid = (unsigned)div_up64(n, 256);
+        KL(ctx);
+        owner_hist_kernel<<<grid, 256, world * sizeof(unsigned int), st>>>(d_digests, n, world, (unsigned long long*)misc);
+        HMSE_LAUNCH_CHECK(ctx);
+        int rc = hmse_exclusive_scan_u64(ctx, misc, misc + world, world, nullptr, st);
+        if (rc) return rc;
+        KL(ctx);
+        owner_scatter_kernel<<<grid, 256, 0, st>>>(d_digests, n, id_base, world, misc + world,
+                                                   (unsigned long long*)(misc + 2 * world), d_records, d_perm);
+        HMSE_LAUNCH_CHECK(ctx);
+    }
+    if (d_counts) HMSE_CUDA(ctx, cudaMemcpyAsync(d_counts, misc, (size_t)world * 8, cudaMemcpyDeviceToDevice, st));
+    return HMSE_OK;
+}
+
 HMSE_API int hmse_dedup_partition(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, uint64_t id_base,
                                     uint32_t world, uint8_t* d_records, uint32_t* d_perm, uint64_t* counts,
                                     void* stream) {
@@ -278,23 +302,8 @@ HMSE_API int hmse_dedup_partition(hmse_ctx* ctx, const uint8_t* d_digests, uint6
     if (world == 0 || world > 512 || !counts) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_partition: bad world/counts");
     for (uint32_t w = 0; w < world; w++) counts[w] = 0;
     if (n == 0) return HMSE_OK;
-    if (!d_digests || !d_records || !d_perm) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_partition: null pointer");
-    if (n > 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_dedup_partition: n exceeds 2^32");
-    // misc: [hist world][offs world][cursor world]
-    HMSE_SCRATCH(ctx, misc, uint64_t*, SLOT_DEDUP_MISC, 3 * (size_t)world * 8);
-    HMSE_CUDA(ctx, cudaMemsetAsync(misc, 0, 3 * (size_t)world * 8, st));
-    const unsigned grid = (unsigned)div_up64(n, 256);
-    KL(ctx);
-    owner_hist_kernel<<<grid, 256, world * sizeof(unsigned int), st>>>(d_digests, n, world,
-                                                                      (unsigned long long*)misc);
-    HMSE_LAUNCH_CHECK(ctx);
-    int rc = hmse_exclusive_scan_u64(ctx, misc, misc + world, world, nullptr, st);
-    if (rc) return rc;
-    KL(ctx);
-    owner_scatter_kernel<<<grid, 256, 0, st>>>(d_digests, n, id_base, world, misc + world,
-                                               (unsigned long long*)(misc + 2 * world), d_records, d_perm);
-    HMSE_LAUNCH_CHECK(ctx);
-    if (int mrc = hmse_mail(ctx, 0, misc, world * 2, st)) return mrc;
+    if (int rc = hmse_dedup_partition_dev(ctx, d_digests, n, id_base, world, d_records, d_perm, nullptr, st)) return rc;
+    if (int mrc = hmse_mail(ctx, 0, ctx->slot[SLOT_DEDUP_MISC], world * 2, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     for (uint32_t w = 0; w < world; w++) counts[w] = ctx->pinned[w];
     return HMSE_OK;
@@ -310,7 +319,8 @@ HMSE_API int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_
     if (m >= 0x7FFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "dedup: more than 2^31-1 records per table");
     uint64_t cap = 1024;
     while (cap < 2 * m) cap <<= 1;
-    HMSE_SCRATCH(ctx, table, uint32_t*, SLOT_DEDUP_TABLE, cap * sizeof(uint32_t) + m * sizeof(uint64_t));
+    // its own slot: a streaming session (hmse_dedup_begin / append) on the same ctx keeps its table
+    HMSE_SCRATCH(ctx, table, uint32_t*, SLOT_DEDUP_OWNER, cap * sizeof(uint32_t) + m * sizeof(uint64_t));
     unsigned long long* min_gid = (unsigned long long*)(table + cap);
     HMSE_CUDA(ctx, cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t) + m * sizeof(uint64_t), st));
     const unsigned grid = (unsigned)div_up64(m, 256);

@@ -114,13 +114,12 @@ struct DeflArgs {
     uint8_t* hdrs;           // [batch job][640] dynamic header bytes
     ChunkRec* recs;          // [batch job]
     unsigned int* counter;
+    unsigned long long* stat;  // per-call counters in ctx scratch: [0] token words, [1] input bytes, [2] chunks parsed
 };
 
 // Per-phase cycle counters of parse_kernel (thread 0 of every CTA, summed over chunks); read by
 // hmse_debug_deflate_prof.  A dozen clock reads per chunk: negligible.
 __device__ unsigned long long g_prof[16];
-// [0] token words, [1] input bytes, [2] chunks parsed since the host last cleared them (hmse_compress_stats)
-__device__ unsigned long long g_stat[4];
 #define PROF(i)                                                     \
     if (t == 0) {                                                   \
         const long long now__ = clock64();                          \
@@ -769,9 +768,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             rec.bits = 0;
             rec.pad = 0;
             a.recs[bj] = rec;
-            atomicAdd(&g_stat[0], (unsigned long long)n_words);
-            atomicAdd(&g_stat[1], (unsigned long long)n);
-            atomicAdd(&g_stat[2], 1ull);
+            atomicAdd(&a.stat[0], (unsigned long long)n_words);
+            atomicAdd(&a.stat[1], (unsigned long long)n);
+            atomicAdd(&a.stat[2], 1ull);
         }
         PROF(8)
         if (t == 0) atomicAdd(&g_prof[15], 1ull);
@@ -1639,24 +1638,33 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x *= 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
+// out[2] = the Adler-32 of the same bytes (sum of bytes and position-weighted sum, n <= 32768: no overflow in 64 bits), so
+// that a cached dictionary is only reused when fingerprint, length AND checksum agree.
 __global__ void __launch_bounds__(256) dict_fingerprint_kernel(const uint8_t* __restrict__ d, uint32_t n, uint64_t* __restrict__ out) {
-    __shared__ uint64_t s0[256], s1[256];
-    uint64_t a = 0, b = 0;
+    __shared__ uint64_t s0[256], s1[256], s2[256], s3[256];
+    uint64_t a = 0, b = 0, sa = 0, sb = 0;
     for (uint32_t i = threadIdx.x; i < n; i += 256) {
         const uint64_t x = ((uint64_t)i << 8) | d[i];
         a += mix64(x + 0x9E3779B97F4A7C15ull);
         b += mix64(x ^ 0xD6E8FEB86659FD93ull);
+        sa += d[i];
+        sb += (uint64_t)(n - i) * d[i];
     }
     s0[threadIdx.x] = a;
     s1[threadIdx.x] = b;
+    s2[threadIdx.x] = sa;
+    s3[threadIdx.x] = sb;
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 256; i++) {
             a += s0[i];
             b += s1[i];
+            sa += s2[i];
+            sb += s3[i];
         }
         out[0] = a;
         out[1] = b;
+        out[2] = (((uint64_t)n + sb) % 65521u) << 16 | ((1 + sa) % 65521u);
     }
 }
 
@@ -1683,7 +1691,8 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
     HMSE_LAUNCH_CHECK(ctx);
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     const uint64_t fp0 = ctx->pinned[0], fp1 = ctx->pinned[1];
-    if (hd->valid && hd->len == dict_len && hd->fp[0] == fp0 && hd->fp[1] == fp1) {
+    const uint32_t dev_adler = (uint32_t)ctx->pinned[2];
+    if (hd->valid && hd->len == dict_len && hd->fp[0] == fp0 && hd->fp[1] == fp1 && hd->adler == dev_adler) {
         *adler = hd->adler;
         return HMSE_OK;
     }
@@ -1748,7 +1757,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     *total = 0;
     if (dict_len > DICT_MAX) HMSE_FAIL(ctx, HMSE_E_INVAL, "dict_len must be <= 32768");
     if (dict_len && !d_zdict) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_zdict is null");
-    if (level < 0 || level > 9) HMSE_FAIL(ctx, HMSE_E_INVAL, "level must be 0..9");
+    if (level != 0 && level != 6)
+        HMSE_FAIL(ctx, HMSE_E_INVAL, "level must be 0 (stored blocks) or 6 (the match search is tuned against zlib level 6; "
+                                     "other levels are not implemented)");
     if (m >= 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "too many chunks in one call");
     if (m == 0) {
         HMSE_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, 8, st));
@@ -1762,9 +1773,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         int rc = ensure_dict(ctx, d_zdict, dict_len, &dict_adler, st);
         if (rc) return rc;
     }
-    // misc: [slot_size m][slot_off m][sizes m+1][lists 4m u32][list_n 4 u32][totals][counters]
+    // misc: [slot_size m][slot_off m][sizes m+1][lists 4m u32][list_n 4 u32][totals 2 u64][stat 4 u64][counters]
     const size_t n_counters = m + 8;   // one work counter per batch; a long chunk may be a batch of its own
-    const size_t misc_bytes = (3 * m + 2) * 8 + 4 * m * 4 + 64 + n_counters * 4 + 64;
+    const size_t misc_bytes = (3 * m + 2) * 8 + 4 * m * 4 + 64 + 32 + n_counters * 4 + 64;
     HMSE_SCRATCH(ctx, misc, uint8_t*, SLOT_DEFLATE_MISC, misc_bytes);
     uint64_t* slot_size = (uint64_t*)misc;
     uint64_t* slot_off = slot_size + m;
@@ -1772,8 +1783,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     uint32_t* lists = (uint32_t*)(sizes + m + 1);
     uint32_t* list_n = lists + 4 * m;
     uint64_t* d_tot = (uint64_t*)(((uintptr_t)(list_n + 4) + 7) & ~(uintptr_t)7);  // [stage total, out total]
-    unsigned int* counters = (unsigned int*)(d_tot + 2);
-    HMSE_CUDA(ctx, cudaMemsetAsync(list_n, 0, 48 + n_counters * 4, st));
+    unsigned long long* d_stat = (unsigned long long*)(d_tot + 2);   // per call and per ctx: contexts never share counters
+    unsigned int* counters = (unsigned int*)(d_stat + 4);
+    HMSE_CUDA(ctx, cudaMemsetAsync(list_n, 0, (size_t)((uint8_t*)(counters + n_counters) - (uint8_t*)list_n), st));
     KL(ctx);
     classify_kernel<<<(unsigned)div_up64(m, 256), 256, 0, st>>>(start0, d_cuts, d_select, m, slot_size, lists, list_n);
     HMSE_LAUNCH_CHECK(ctx);
@@ -1801,6 +1813,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     a.stage = stage;
     a.slot_off = slot_off;
     a.sizes = sizes;
+    a.stat = d_stat;
 
     const size_t sm_parse[N_CLASS] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_MEDIUM, false), parse_smem(NMAX_LARGE, false)};
     const size_t sm_huff = sizeof(HuffSm) * HUFF_WARPS;
@@ -1922,10 +1935,6 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         if (end) ctx->pev_n++;                                                                \
     }                                                                                          \
     if (end) n_parse++
-    {
-        unsigned long long z[4] = {0, 0, 0, 0};
-        HMSE_CUDA(ctx, cudaMemcpyToSymbolAsync(g_stat, z, sizeof(z), 0, cudaMemcpyHostToDevice, st));
-    }
     HT_BEGIN(ctx, HT_DEFLATE, st);
     uint32_t ci = 0;
     const uint32_t hmax = (uint32_t)ctx->sm_count * 3, emax = (uint32_t)ctx->sm_count * 8;
@@ -2005,11 +2014,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     rc = hmse_exclusive_scan_u64(ctx, sizes, d_offsets, m + 1, d_tot + 1, st);
     if (rc) return rc;
     if (int mrc = hmse_mail(ctx, 0, d_tot + 1, 2, st)) return mrc;
-    {
-        void* gs = nullptr;
-        HMSE_CUDA(ctx, cudaGetSymbolAddress(&gs, g_stat));
-        if (int mrc = hmse_mail(ctx, 8, gs, 6, st)) return mrc;
-    }
+    if (int mrc = hmse_mail(ctx, 8, d_stat, 6, st)) return mrc;
     HMSE_CUDA(ctx, cudaStreamSynchronize(st));
     *total = mail[0];
     ctx->stat[0] = n_parse;

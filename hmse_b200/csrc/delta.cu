@@ -270,6 +270,7 @@ struct ApplyArgs {
     const uint64_t* delta_off;
     uint64_t m;
     const uint8_t* base;
+    uint64_t base_bytes;
     const uint64_t* base_off;
     const uint32_t* base_len;
     uint8_t* out;
@@ -290,7 +291,8 @@ __global__ void __launch_bounds__(256) delta_apply_kernel(ApplyArgs a) {
         uint8_t* O = a.out + a.out_off[j];
         const uint64_t n64 = a.out_off[j + 1] - a.out_off[j];
         uint32_t st = 0;
-        if (dl64 > 0xFFFFFFFFull || n64 > 0xFFFFFFFFull) st = 2;
+        if (dl64 > 0xFFFFFFFFull || n64 > 0xFFFFFFFFull) st = 2;   // (also offsets that run backwards)
+        if (a.base_off[j] > a.base_bytes || nb > a.base_bytes - a.base_off[j]) st = 3;   // base range outside d_base
         const uint32_t dl = (uint32_t)dl64, n = (uint32_t)n64;
         uint32_t i = 0, o = 0, expect = 0;
         // varint at D[i]: lanes 0..4 fetch one byte each
@@ -416,8 +418,8 @@ HMSE_API int hmse_delta_encode(hmse_ctx* ctx, const uint8_t* d_data, uint64_t st
 }
 
 HMSE_API int hmse_delta_apply(hmse_ctx* ctx, const uint8_t* d_delta, const uint64_t* d_delta_off, uint64_t m,
-                              const uint8_t* d_base, const uint64_t* d_base_off, const uint32_t* d_base_len, uint8_t* d_out,
-                              const uint64_t* d_out_off, uint32_t* d_status, uint64_t* n_bad, void* stream) {
+                              const uint8_t* d_base, uint64_t base_bytes, const uint64_t* d_base_off, const uint32_t* d_base_len,
+                              uint8_t* d_out, const uint64_t* d_out_off, uint32_t* d_status, uint64_t* n_bad, void* stream) {
     if (!ctx) return HMSE_E_INVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (n_bad) *n_bad = 0;
@@ -426,7 +428,7 @@ HMSE_API int hmse_delta_apply(hmse_ctx* ctx, const uint8_t* d_delta, const uint6
         HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_apply: null pointer");
     HMSE_SCRATCH(ctx, bad, unsigned long long*, SLOT_DELTA_BAD, 16);
     HMSE_CUDA(ctx, cudaMemsetAsync(bad, 0, 8, st));
-    ApplyArgs aa{d_delta, d_delta_off, m, d_base, d_base_off, d_base_len, d_out, d_out_off, d_status, bad};
+    ApplyArgs aa{d_delta, d_delta_off, m, d_base, base_bytes, d_base_off, d_base_len, d_out, d_out_off, d_status, bad};
     const uint64_t want = div_up64(m, 8), cap = (uint64_t)ctx->sm_count * 8;
     KL(ctx);
     delta_apply_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(aa);

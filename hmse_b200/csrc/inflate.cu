@@ -204,10 +204,17 @@ __global__ void __launch_bounds__(IW * 32) inflate_kernel(InfArgs a) {
         if (lane == 0) j = atomicAdd(a.counter, 1u);
         j = __shfl_sync(0xffffffffu, j, 0);
         if (j >= a.m) break;
-        const uint8_t* in = a.blob + a.offs[j];
-        const uint8_t* in_end = a.blob + a.offs[j + 1];
-        uint8_t* out = a.out + a.out_offs[j];
-        const uint32_t out_len = (uint32_t)(a.out_offs[j + 1] - a.out_offs[j]);
+        // the offsets come from the caller (an archive that may be damaged): a stream or an output range that runs
+        // backwards, or an output range beyond 32 bits, is reported and nothing is read or written for it
+        const uint64_t o0 = a.offs[j], o1 = a.offs[j + 1], q0 = a.out_offs[j], q1 = a.out_offs[j + 1];
+        if (o1 < o0 || q1 < q0 || q1 - q0 > 0xFFFFFFFFull) {
+            if (lane == 0) a.status[j] = o1 < o0 ? INF_BAD_HEADER : INF_OVERRUN;
+            continue;
+        }
+        const uint8_t* in = a.blob + o0;
+        const uint8_t* in_end = a.blob + o1;
+        uint8_t* out = a.out + q0;
+        const uint32_t out_len = (uint32_t)(q1 - q0);
         uint32_t status = INF_OK;
         uint32_t pos = 0;
         BitReader br;
@@ -455,7 +462,7 @@ HMSE_API int hmse_inflate(hmse_ctx* ctx, const uint8_t* d_blob, const uint64_t* 
     cudaStream_t st = (cudaStream_t)stream;
     if (n_bad) *n_bad = 0;
     if (m == 0) return HMSE_OK;
-    if (!d_blob || !d_offsets || !d_out_offsets || !d_status) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_inflate: null pointer");
+    if (!d_blob || !d_offsets || !d_out_offsets || !d_status || !d_out) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_inflate: null pointer");
     if (dict_len > 32768) HMSE_FAIL(ctx, HMSE_E_INVAL, "dict_len must be <= 32768");
     if (dict_len && !d_zdict) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_zdict is null");
     if (m >= 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "too many streams in one call");

@@ -71,6 +71,7 @@ class Ingest:
         """l4: also run the similarity layer; first occurrences that keep a delta are not compressed (`select` lists
         the chunks of the chunk store only) and `base` / `delta_blob` / `delta_offsets` describe the deltas."""
         ctx = self.ctx
+        d = ctx.stage(d)     # unchanged when it is aligned and has slack behind it; re-staged otherwise
         cuts = ctx.chunk(d, self.cdc)
         digests = ctx.digest(d, cuts)
         canon, first = ctx.dedup(digests)
@@ -423,9 +424,22 @@ class ShardedIngest(Ingest):
     """Rank r holds stream bytes [lo_r, hi_r + max_size) (the last rank up to the stream end).
     Chunks are owned by the shard they start in; global ids follow stream order."""
 
-    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, group=None):
+    def __init__(self, ctx: Context, cdc: CDCConfig = CDCConfig(), zdict=b"", level: int = 6, group=None,
+                 transport: str = "auto"):
+        """transport: "c" = the exchange steps run inside the library on its own NCCL communicator (hmse_chunk_sharded,
+        hmse_dedup_global: one host round trip per step); "torch" = the same protocol spelled with torch.distributed
+        collectives (hmse_b200/sharding.py - the form the gloo tests exercise on CPU); "auto" = "c" when the process
+        group runs on NCCL."""
         super().__init__(ctx, cdc, zdict, level)
         self.group = group
+        if transport == "auto":
+            import torch.distributed as dist
+            transport = "c" if dist.is_initialized() and dist.get_backend(group) == "nccl" else "torch"
+        if transport not in ("c", "torch"):
+            raise ValueError("transport must be 'auto', 'c' or 'torch'")
+        self.transport = transport
+        if transport == "c":
+            ctx.comm_init(group)
         self._s_out = None
         self._s_in = None
         self._stage = [None, None]
@@ -442,30 +456,36 @@ class ShardedIngest(Ingest):
         ctx = self.ctx
         dev = ctx.tdev
         world = dist.get_world_size(self.group)
-        ctx.chunk_scan(d, self.cdc)
-        own = d.numel() if eof else n_own
-        cuts, entry, _ = sharding.stitch_cuts(lambda e: ctx.chunk_resolve(d, self.cdc, n_own, eof, e), own, dev, self.group)
-        n = cuts.numel()
-        digests = ctx.digest(d, cuts, start0=entry)
-        counts_all = sharding._all_gather_i64(n, dev, self.group)
-        id_base = sum(counts_all[:dist.get_rank(self.group)])
-        # partition -> all-to-all -> owner table -> all-to-all back -> scatter
-        rec = ctx.empty(max(n, 1) * 40, torch.uint8)
-        perm = ctx.empty(max(n, 1), torch.int32)
-        cnt = (C.c_uint64 * world)()
-        ctx.check(ctx.lib.hmse_dedup_partition(ctx.h, digests.data_ptr(), n, id_base, world, rec.data_ptr(), perm.data_ptr(),
-                                               cnt, ctx.stream))
+        if self.transport == "c":
+            cuts, entry, id_base, _ = ctx.chunk_sharded(d, self.cdc, n_own, eof)
+            n = cuts.numel()
+            digests = ctx.digest(d, cuts, start0=entry)
+            canon, first = ctx.dedup_global(digests, id_base)
+        else:
+            ctx.chunk_scan(d, self.cdc)
+            own = d.numel() if eof else n_own
+            cuts, entry, _ = sharding.stitch_cuts(lambda e: ctx.chunk_resolve(d, self.cdc, n_own, eof, e), own, dev, self.group)
+            n = cuts.numel()
+            digests = ctx.digest(d, cuts, start0=entry)
+            counts_all = sharding._all_gather_i64(n, dev, self.group)
+            id_base = sum(counts_all[:dist.get_rank(self.group)])
+            # partition -> all-to-all -> owner table -> all-to-all back -> scatter
+            rec = ctx.empty(max(n, 1) * 40, torch.uint8)
+            perm = ctx.empty(max(n, 1), torch.int32)
+            cnt = (C.c_uint64 * world)()
+            ctx.check(ctx.lib.hmse_dedup_partition(ctx.h, digests.data_ptr(), n, id_base, world, rec.data_ptr(), perm.data_ptr(),
+                                                   cnt, ctx.stream))
 
-        def owner(recv: torch.Tensor, m: int) -> torch.Tensor:
-            out = ctx.empty(max(m, 1), torch.int64)
-            ctx.check(ctx.lib.hmse_dedup_records(ctx.h, recv.data_ptr(), m, out.data_ptr(), ctx.stream))
-            return out[:m]
+            def owner(recv: torch.Tensor, m: int) -> torch.Tensor:
+                out = ctx.empty(max(m, 1), torch.int64)
+                ctx.check(ctx.lib.hmse_dedup_records(ctx.h, recv.data_ptr(), m, out.data_ptr(), ctx.stream))
+                return out[:m]
 
-        reply = sharding.exchange_dedup(rec[:n * 40], [int(c) for c in cnt], owner, self.group)
-        canon = ctx.empty(max(n, 1), torch.int64)
-        first = ctx.empty(max(n, 1), torch.uint8)
-        ctx.check(ctx.lib.hmse_dedup_scatter(ctx.h, reply.data_ptr(), perm.data_ptr(), n, id_base, canon.data_ptr(),
-                                             first.data_ptr(), ctx.stream))
+            reply = sharding.exchange_dedup(rec[:n * 40], [int(c) for c in cnt], owner, self.group)
+            canon = ctx.empty(max(n, 1), torch.int64)
+            first = ctx.empty(max(n, 1), torch.uint8)
+            ctx.check(ctx.lib.hmse_dedup_scatter(ctx.h, reply.data_ptr(), perm.data_ptr(), n, id_base, canon.data_ptr(),
+                                                 first.data_ptr(), ctx.stream))
         canon, first = canon[:n], first[:n]
         base = dblob = doffs = None
         stored = first
@@ -603,9 +623,15 @@ class ShardedSimilarity:
     keys travel to the band's owner (band % world) with one all-to-all, and the owner sorts its bands over ALL
     chunks of the stream - (band, key, global id) groups equal to oracle.buckets on the whole stream, band-sliced."""
 
-    def __init__(self, ctx: Context, cfg=None, group=None):
+    def __init__(self, ctx: Context, cfg=None, group=None, transport: str = "auto"):
         from .config import SimConfig
         self.ctx, self.cfg, self.group = ctx, cfg or SimConfig(), group
+        if transport == "auto":
+            import torch.distributed as dist
+            transport = "c" if dist.is_initialized() and dist.get_backend(group) == "nccl" else "torch"
+        self.transport = transport
+        if transport == "c":
+            ctx.comm_init(group)
 
     def run(self, d: torch.Tensor, cuts: torch.Tensor, start0: int = 0):
         """Returns (sig int32 [n, n_perm], keys int64 [n, bands], (band int32, key int64, id int64) of the owned bands)."""
@@ -613,7 +639,11 @@ class ShardedSimilarity:
         ctx = self.ctx
         sig = ctx.minhash(d, cuts, self.cfg, start0)
         keys = ctx.lsh_keys(sig, self.cfg)
-        owned, mine, _ = sharding.exchange_lsh(keys, self.group)
+        if self.transport == "c":
+            owned, _ = ctx.lsh_exchange(keys)              # hmse_lsh_exchange: ncclSend / ncclRecv inside the library
+            mine = list(range(owned.shape[1]))
+        else:
+            owned, mine, _ = sharding.exchange_lsh(keys, self.group)
         if owned.shape[0] == 0 or not mine:
             e32, e64 = ctx.empty(0, torch.int32), ctx.empty(0, torch.int64)
             return sig, keys, (e32, e64, e64.clone())

@@ -35,8 +35,9 @@ extern "C" {
 #define HMSE_E_CAPACITY (-2) /* an output buffer is too small; needed size is returned */
 #define HMSE_E_CUDA (-3)     /* CUDA runtime error (text in hmse_last_error)   */
 #define HMSE_E_NOMEM (-4)    /* scratch allocation failed                      */
+#define HMSE_E_NCCL (-5)     /* NCCL is missing or a collective failed (text in hmse_last_error) */
 
-#define HMSE_ABI_VERSION 1
+#define HMSE_ABI_VERSION 2
 
 typedef struct hmse_ctx hmse_ctx;
 
@@ -71,6 +72,7 @@ uint64_t hmse_scratch_bytes(hmse_ctx* ctx);
 #define HMSE_T_LSH 7
 #define HMSE_T_INFLATE 8
 #define HMSE_T_DELTA 9
+#define HMSE_T_EXCHANGE 10 /* the NCCL part of the last hmse_chunk_sharded / hmse_dedup_global / hmse_lsh_exchange */
 int hmse_timing(hmse_ctx* ctx, int enable);
 int hmse_timing_ms(hmse_ctx* ctx, int id, float* ms);
 /* Kernels launched through this ctx since hmse_create. */
@@ -124,7 +126,7 @@ int hmse_dedup(hmse_ctx* ctx, const uint8_t* d_digests, uint64_t n, int64_t* d_c
  * (whose first n_prev rows must be the ones appended so far, at the same address) and writes
  * d_canon[i - n_prev] = smallest j <= i with digest j == digest i (absolute indices),
  * d_is_first[i - n_prev] = (canon == i).  Results equal hmse_dedup over the whole array.
- * hmse_dedup and hmse_dedup_records use the same table: one table per ctx at a time. */
+ * hmse_dedup uses the same table (it ends a streaming session); hmse_dedup_records has its own. */
 int hmse_dedup_begin(hmse_ctx* ctx, uint64_t max_chunks, void* stream);
 int hmse_dedup_append(hmse_ctx* ctx, const uint8_t* d_digests_all, uint64_t n_prev, uint64_t n_new,
                       int64_t* d_canon, uint8_t* d_is_first, void* stream);
@@ -148,6 +150,50 @@ int hmse_dedup_records(hmse_ctx* ctx, const uint8_t* d_records, uint64_t m, uint
 int hmse_dedup_scatter(hmse_ctx* ctx, const uint64_t* d_reply, const uint32_t* d_perm, uint64_t n,
                        uint64_t id_base, int64_t* d_canon, uint8_t* d_is_first, void* stream);
 
+/* ---- Multi-GPU: one process per GPU, NCCL over NVLink (SURVEY.md section 8b "multi-GPU variant takes ncclComm_t and a
+ *      global id base", 8e).  The reference is a single MCU (README.md:141-153) and has no counterpart; these entry
+ *      points are what a host binding calls where the single-GPU flow calls hmse_chunk / hmse_dedup.
+ *      `comm` is an ncclComm_t passed as void* (NCCL types stay out of this header) - the caller's own communicator, or
+ *      NULL for the one hmse_comm_init created on this ctx.  NCCL is bound at run time (libnccl.so.2); without it these
+ *      calls fail with HMSE_E_NCCL and everything else works.  Every rank of the communicator must make the same call. -- */
+#define HMSE_UNIQUE_ID_BYTES 128
+/* Rank 0: a fresh ncclUniqueId (128 bytes) to hand to every rank by any side channel. */
+int hmse_comm_unique_id(uint8_t* out128);
+/* ncclCommInitRank on ctx's device; the communicator belongs to ctx (freed by hmse_comm_destroy / hmse_destroy). */
+int hmse_comm_init(hmse_ctx* ctx, const uint8_t* id128, int world, int rank);
+int hmse_comm_destroy(hmse_ctx* ctx);
+/* Size, rank and NCCL version (e.g. 22809) of `comm` (NULL: ctx's own); any out pointer may be null. */
+int hmse_comm_info(hmse_ctx* ctx, void* comm, int* world, int* rank, int* nccl_version);
+/* out[4 * r + q] (host) = vals4[q] of rank r: one ncclAllGather, one mailbox read (synchronises `stream`). */
+int hmse_allgather_u64(hmse_ctx* ctx, void* comm, const uint64_t* vals4, uint64_t* out, void* stream);
+
+/* L2 chunking of ONE stream held as contiguous byte-range shards: this rank holds d_data[0:n_avail) = its n_own owned
+ * bytes + max_size bytes of look-ahead (eof != 0: the last shard, n_own is ignored).  Scan, speculative resolve from
+ * offset 0, then rounds of { all-gather exits, re-resolve incrementally from the true entry } until no entry changes.
+ * d_cuts / *n_cuts: the chunks that START in this shard (cuts relative to d_data); *entry = offset of the first one;
+ * *id_base = chunks in the shards before this one; *n_total = chunks of the whole stream.  Concatenated over ranks the
+ * cut lists equal hmse_chunk over the whole stream.  Synchronises `stream`. */
+int hmse_chunk_sharded(hmse_ctx* ctx, void* comm, const uint8_t* d_data, uint64_t n_own, uint64_t n_avail, int eof,
+                       const hmse_cdc_cfg* cfg, uint64_t* d_cuts, uint64_t cap, uint64_t* n_cuts, uint64_t* entry,
+                       uint64_t* id_base, uint64_t* n_total, void* stream);
+/* Global exact dedup (the ChunkIndex rule over the whole stream, README.md:1288-1292): d_canon[i] = smallest GLOBAL id
+ * (id_base + local index on its rank) with the same digest anywhere, d_is_first[i] = (canon == id_base + i).  Records
+ * travel to owner = le32(digest) % world and the answers back with ncclSend / ncclRecv groups on `stream`.
+ * One host round trip (the counts); results are valid after the caller syncs `stream`. */
+int hmse_dedup_global(hmse_ctx* ctx, void* comm, const uint8_t* d_digests, uint64_t n, uint64_t id_base, int64_t* d_canon,
+                      uint8_t* d_is_first, void* stream);
+/* Global LSH bucketing, exchange step: band b is owned by rank b % world.  d_keys[n][bands] (this rank's chunks, stream
+ * order) -> d_owned[*n_total][*bands_owned] = the owned bands' keys of EVERY chunk of the stream, rows in global id
+ * order (feed it to hmse_lsh_buckets with id_base 0; local column c is band rank + c * world).  *id_base = global id
+ * of this rank's first chunk.  d_owned == NULL with owned_cap_rows == 0 only reports the sizes; on HMSE_E_CAPACITY
+ * *n_total holds the rows needed. */
+int hmse_lsh_exchange(hmse_ctx* ctx, void* comm, const uint64_t* d_keys, uint64_t n, uint32_t bands, uint64_t* d_owned,
+                      uint64_t owned_cap_rows, uint64_t* n_total, uint64_t* id_base, uint32_t* bands_owned, void* stream);
+/* Facts about the last exchange on ctx: out4 = {bytes sent to other ranks, bytes received from other ranks, records
+ * (or rows) owned after the exchange, records (rows) contributed}; *rounds = resync rounds of the last
+ * hmse_chunk_sharded (may be null). */
+int hmse_exchange_stats(hmse_ctx* ctx, uint64_t* out4, int* rounds);
+
 /* ---- L1 DEFLATE: replaces mz_deflateInit2 / mz_deflate(FINISH) (README.md:2374, 2378). --- */
 
 /* Worst-case bytes of one zlib stream for a chunk of `len` bytes. */
@@ -155,8 +201,8 @@ uint64_t hmse_compress_bound(uint64_t len);
 
 /* One RFC 1950 stream (FDICT set when dict_len > 0) per selected chunk, packed back to back in
  * d_out in selection order; d_offsets[m+1] are the stream boundaries.  d_select[k] is a chunk
- * index (NULL = chunks 0..m-1).  dict_len <= 32768.  level is accepted for API parity; 1..9 all
- * run the same match search (tuned against zlib level 6).  *total (host) = d_offsets[m].
+ * index (NULL = chunks 0..m-1).  dict_len <= 32768.  level: 6 (match search and lazy rule tuned against zlib
+ * level 6) or 0 (stored blocks); anything else fails with HMSE_E_INVAL.  *total (host) = d_offsets[m].
  * On HMSE_E_CAPACITY *total holds the required out_cap. */
 int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
                   const uint64_t* d_select, uint64_t m, const uint8_t* d_zdict, uint32_t dict_len,
@@ -253,12 +299,13 @@ int hmse_delta_encode(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, con
                       void* stream);
 /* Read path (README.md:2191-2198 "apply patch to decompressed base"): delta j = d_delta[d_delta_off[j] :
  * d_delta_off[j+1]) applied to the raw base d_base[d_base_off[j] : + d_base_len[j]) yields
- * d_out[d_out_off[j] : d_out_off[j+1]).  d_status[j] = 0, or 1 bad varint, 2 bad op length, 3 copy outside the
- * base, 4 literals past the end of the delta, 5 trailing bytes; a bad delta never writes outside its range.
+ * d_out[d_out_off[j] : d_out_off[j+1]).  base_bytes = size of d_base (a base range outside it is status 3).
+ * d_status[j] = 0, or 1 bad varint, 2 bad op length or offsets that run backwards, 3 copy outside the
+ * base, 4 literals past the end of the delta, 5 trailing bytes; a bad delta never reads or writes outside its ranges.
  * *n_bad (may be null) = number of non-zero statuses (synchronises `stream`). */
 int hmse_delta_apply(hmse_ctx* ctx, const uint8_t* d_delta, const uint64_t* d_delta_off, uint64_t m,
-                     const uint8_t* d_base, const uint64_t* d_base_off, const uint32_t* d_base_len, uint8_t* d_out,
-                     const uint64_t* d_out_off, uint32_t* d_status, uint64_t* n_bad, void* stream);
+                     const uint8_t* d_base, uint64_t base_bytes, const uint64_t* d_base_off, const uint32_t* d_base_len,
+                     uint8_t* d_out, const uint64_t* d_out_off, uint32_t* d_status, uint64_t* n_bad, void* stream);
 
 /* ---- Synthetic corpus (bench/test input, not part of the reference path): renders bytes
  *      [byte_off, byte_off + n) of the procedural wiki stream defined in oracle/corpus.py. ---- */

@@ -31,7 +31,7 @@ tests/golden/.
 """
 from .config import CDCConfig, SimConfig, gear_table, PAPER_MASK_S, PAPER_MASK_L  # noqa: F401
 from .cdc import chunk, chunk_naive, chunk_c, next_cut  # noqa: F401
-from .sha import digest, dedup  # noqa: F401
+from .sha import digest, dedup, digest_mt, dedup_fast  # noqa: F401
 from .deflate import compress, inflate_all, make_zdict  # noqa: F401
 from .minhash import (murmur3_32, minhash, minhash_c, band_keys, buckets,  # noqa: F401
                       similarity)

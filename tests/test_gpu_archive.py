@@ -117,3 +117,36 @@ def test_l4_archive_records_equal_oracle_and_roundtrip(ctx, corpus8):
     bad[len(buf) - ar.delta_store.size + 9] = 0xFF
     with pytest.raises(ValueError):
         archive.restore(archive.Archive.frombytes(bytes(bad)), ctx=ctx)
+
+
+def test_cross_shard_canon_is_rejected_not_dereferenced(ctx, corpus8):
+    """A shard result of ShardedIngest carries GLOBAL ids in canon: a chunk whose first occurrence lies in an earlier
+    shard (canon < id_base) or a later range has no record in this shard's store.  hmse_index_build must report it
+    (HMSE_E_INVAL) instead of indexing its slot table with a wrapped value (archive.cu:25)."""
+    import copy
+    import hmse_b200
+    from hmse_b200 import archive
+    zd = corpus.zdict()
+    data = np.concatenate([corpus8[:2 << 20], corpus8[:1 << 20]])
+    r = _ingest(ctx, data, zd)
+    # the same result seen as a shard whose global ids start at 1000: canon shifted with it - fine, records unchanged
+    ok = copy.copy(r)
+    ok.id_base = 1000
+    ok.canon = r.canon + 1000
+    a0, a1 = archive.build(r, zd, ctx=ctx), archive.build(ok, zd, ctx=ctx)
+    assert np.array_equal(a0.index, a1.index) and np.array_equal(a0.pointers, a1.pointers)
+    for bad_value in (999, 5, 1000 + r.n_chunks, -1):
+        bad = copy.copy(ok)
+        bad.canon = ok.canon.clone()
+        bad.canon[r.n_chunks // 2] = bad_value
+        with pytest.raises(hmse_b200.HmseError) as ei:
+            archive.build(bad, zd, ctx=ctx)
+        assert ei.value.code == -1 and "cross-shard" in str(ei.value)
+    # a chunk that resolves to a local chunk which is not in the store (not selected)
+    bad = copy.copy(r)
+    dup = int((~r.is_first).nonzero()[0])
+    bad.canon = r.canon.clone()
+    bad.canon[0] = dup
+    with pytest.raises(hmse_b200.HmseError):
+        archive.build(bad, zd, ctx=ctx)
+    assert archive.restore(archive.build(r, zd, ctx=ctx), ctx=ctx).tobytes() == data.tobytes()   # the ctx still works

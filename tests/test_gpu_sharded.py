@@ -31,6 +31,17 @@ n_avail = (total - rank * per) if eof else per + cfg.max_size
 d = gen.generate(n_avail, byte_off=rank * per)
 zd = ctx.stage(pc.zdict())
 res = hmse_b200.ShardedIngest(ctx, cfg, zd).run(d, per, eof)
+assert hmse_b200.ShardedIngest(ctx, cfg, zd).transport == "c"      # the exchange runs inside the library (csrc/comm.cu)
+xs = ctx.exchange_stats()
+assert xs["contributed"] == res.n_chunks and (world == 1 or xs["bytes_sent"] > 0)
+# the same protocol spelled with torch.distributed collectives (the form the gloo tests cover) gives the same result
+rt = hmse_b200.ShardedIngest(ctx, cfg, zd, transport="torch").run(d, per, eof)
+assert rt.entry == res.entry and rt.id_base == res.id_base
+assert torch.equal(rt.cuts, res.cuts) and torch.equal(rt.canon, res.canon) and torch.equal(rt.is_first, res.is_first)
+assert torch.equal(rt.digests, res.digests) and torch.equal(rt.blob, res.blob)
+st_, kt_, (bt_, kkt_, it_) = hmse_b200.ShardedSimilarity(ctx, transport="torch").run(d, res.cuts, start0=res.entry)
+sc_, kc_, (bc_, kkc_, ic_) = hmse_b200.ShardedSimilarity(ctx, transport="c").run(d, res.cuts, start0=res.entry)
+assert torch.equal(bt_, bc_) and torch.equal(kkt_, kkc_) and torch.equal(it_, ic_)
 pipe = hmse_b200.ShardedIngest(ctx, cfg, zd)
 hres = pipe.run(d, per, eof, host=pipe.host_buffers(n_avail), groups=3)
 assert np.array_equal(hres.cuts.numpy(), res.cuts.cpu().numpy()) and np.array_equal(hres.canon.numpy(), res.canon.cpu().numpy())

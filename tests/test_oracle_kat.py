@@ -263,3 +263,19 @@ def test_archive_records_and_pure_zlib_restore():
     assert int.from_bytes(ptr[i, 6:8].tobytes(), "little") + 1 == int(cuts[i] - cuts[i - 1])
     buf = archive.pack(zd, idx, ptr, blob, data.size)
     assert buf[:8] == b"HMSEARC1" and archive.restore(buf) == data.tobytes()
+
+
+def test_digest_mt_and_dedup_fast_equal_the_plain_oracle():
+    """The threaded / sort-based forms used for the full-size parity checks are the same functions."""
+    from oracle import corpus
+    d = corpus.generate(3 << 20)
+    d = np.concatenate([d, d[:1 << 20], d[(1 << 19):(3 << 19)]])
+    cuts = oracle.chunk_c(d)
+    a = oracle.digest(d, cuts)
+    assert np.array_equal(a, oracle.digest_mt(d, cuts)) and np.array_equal(a, oracle.digest_mt(d, cuts, threads=3))
+    assert np.array_equal(oracle.digest(d, cuts[5:], start0=int(cuts[4])), oracle.digest_mt(d, cuts[5:], start0=int(cuts[4])))
+    c1, f1 = oracle.dedup(a)
+    c2, f2 = oracle.dedup_fast(a)
+    assert np.array_equal(c1, c2) and np.array_equal(f1, f2) and 0 < f1.sum() < f1.size
+    e = oracle.dedup_fast(np.zeros((0, 32), dtype=np.uint8))
+    assert e[0].size == 0 and e[1].size == 0
