@@ -525,7 +525,55 @@ def run_ours(args):
     #      band keys -> buckets -> base selection -> delta coding with the 20 % rule, then the read path: every kept
     #      delta is applied to its base on the device and the SHA-256 of the result must equal the chunk's digest ----
     l4 = None
-    if not args.no_l4:
+    if not args.no_l4 and world > 1:
+        # N > 1: ONE LSH index over the whole stream (ShardedIngest.similarity_delta_global): band keys to the band owners,
+        # heads back, roots gathered, bases that live on another GPU fetched over NCCL, then the delta coding; verified by
+        # applying every kept delta to its base (local chunk or fetched bytes) and comparing SHA-256 with the chunk's digest
+        sim = hmse_b200.SimConfig()
+        first_u8 = res.is_first.view(torch.uint8).contiguous()
+        g = None
+        for l4_pass in range(2):
+            g = None
+            torch.cuda.synchronize()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            g = pipe.similarity_delta_global(d, cuts, first_u8, int(res.entry), int(res.id_base), sim, 4)
+            g1.record()
+            torch.cuda.synchronize()
+        l4_ms = max_over_ranks(g0.elapsed_time(g1))
+        kept = torch.nonzero(g["base_gid"] >= 0).view(-1)
+        same_l4, dbad = True, 0
+        if kept.numel():
+            bl_ = g["base_loc"][kept]
+            is_ext = bl_ >= n_chunks
+            both = torch.cat([d, g["ext_data"]])
+            e_ = (bl_ - n_chunks).clamp(min=0)
+            bo = torch.where(is_ext, d.numel() + g["ext_off"][e_], starts[bl_.clamp(max=n_chunks - 1)]).contiguous()
+            bl = torch.where(is_ext, g["ext_off"][e_ + 1] - g["ext_off"][e_], lens[bl_.clamp(max=n_chunks - 1)]).to(torch.int32).contiguous()
+            out_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens[kept], 0)])
+            doff_k = torch.cat([g["delta_offsets"][kept], g["delta_offsets"][-1:]])
+            rebuilt, dstatus, dbad = ctx.delta_apply(g["delta_blob"], doff_k, both, bo, bl, out_off)
+            same_l4 = bool(torch.equal(ctx.digest(rebuilt, out_off[1:].contiguous()), res.digests[kept])) and dbad == 0
+            del both, rebuilt
+        in_store = (g["base_gid"][res.select] >= 0)
+        clen = res.offsets[1:] - res.offsets[:-1]
+        kept_deflated = int(clen[in_store].sum())
+        n_cross = int((g["base_loc"][kept] >= n_chunks).sum()) if kept.numel() else 0
+        l4 = {"what": "GLOBAL L4 over the %d x %.0f GB stream: MinHash of the first occurrences on their own rank, band keys to the band "
+                      "owners (hmse_lsh_exchange), bucket heads back (hmse_alltoallv), roots gathered, remote base chunks fetched, delta "
+                      "coding with the 20 %% rule; second of two passes, whole layer timed with CUDA events, max over ranks" % (world, args.gb),
+              "ms": l4_ms, "GB/s": total / (l4_ms * 1e-3) / 1e9,
+              "deltas_kept": int(sum_over_ranks(int(kept.numel()))), "deltas_with_base_on_another_gpu": int(sum_over_ranks(n_cross)),
+              "remote_bases_fetched": int(sum_over_ranks(g["n_remote"])), "remote_base_bytes": int(sum_over_ranks(int(g["ext_off"][-1]))),
+              "kept_raw_bytes": int(sum_over_ranks(int(lens[kept].sum()) if kept.numel() else 0)),
+              "delta_bytes": int(sum_over_ranks(int(g["delta_blob"].numel()))),
+              "same_chunks_deflated_bytes": int(sum_over_ranks(kept_deflated)),
+              "store_bytes_saved": int(sum_over_ranks(kept_deflated - int(g["delta_blob"].numel()) - 8 * int(kept.numel()))),
+              "read_path": {"deltas_applied": int(sum_over_ranks(int(kept.numel()))), "failed": int(sum_over_ranks(int(dbad))),
+                            "digests_equal": bool(sum_over_ranks(0 if same_l4 else 1) == 0)}}
+        del g
+    elif not args.no_l4:
         sim = hmse_b200.SimConfig()
         usel = res.select                     # first occurrences: the only chunks that are hashed (README.md:1553-1556)
         ones = torch.ones(usel.numel(), dtype=torch.uint8, device=dev)
@@ -619,11 +667,18 @@ def run_ours(args):
         k_e2e = max(1, min(args.steps, 5))
         e2e_steps(1)
         barrier()
+        if world > 1:
+            pipe.trace = []
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         e2e_steps(k_e2e)
         a1.record()
         barrier()
+        timeline = None
+        if world > 1 and pipe.trace:
+            # rank 0, per batch, ms since the timed region began: copy-in start / end, pipeline start, all results on the host
+            timeline = [[round(a0.elapsed_time(ev), 1) for ev in tup] for tup in pipe.trace]
+            pipe.trace = None
         ems = max_over_ranks(a0.elapsed_time(a1)) / k_e2e
         # ---- the host's ceiling for this byte mix: the same host->device and device->host bytes per step, copies only
         #      (no kernels), both directions at once, all ranks at once ----
@@ -658,6 +713,7 @@ def run_ours(args):
         e2e = {"value": total / (ems * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(n_avail)),
                "d2h_bytes_per_step": int(sum_over_ranks(d2h)), "ms_per_step": ems, "steps": k_e2e, "api": api,
                "host_ceiling_GBps": total / (cms * 1e-3) / 1e9, "host_ceiling_ms_per_step": cms,
+               "timeline_rank0_ms": timeline,
                "frac_of_host_ceiling": cms / ems,
                "host_ceiling_what": "the same pinned buffers and bytes per step copied host->device and device->host on two "
                                     "streams with no kernels, all ranks at once, max over ranks"}
@@ -767,6 +823,7 @@ def run_config4(args):
         run = lambda buf: pipe.run(buf)  # noqa: E731
     res = None
     for _ in range(args.warmup):
+        res = None            # (a shard's blob is tens of GB: drop the previous step's before the next is allocated)
         res = run(d)
     lib.hmse_timing(ctx.h, 1)
     names = ["scan", "resolve", "sha256", "dedup", "deflate", "pack"]
@@ -780,6 +837,7 @@ def run_config4(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
+        res = None
         res = run(d)
         f = C.c_float(0)
         for i, k in enumerate(names):

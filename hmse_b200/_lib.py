@@ -57,6 +57,7 @@ SIGNATURES = {
     "hmse_dedup_scatter": (_I, [_P, _P, _P, _U64, _U64, _P, _P, _P]),
     "hmse_compress_bound": (_U64, [_U64]),
     "hmse_compress": (_I, [_P, _P, _U64, _P, _P, _U64, _P, _U32, _I, _P, _U64, _P, _PU64, _P]),
+    "hmse_compress_pack": (_I, [_P, _P, _U64, _P, _U64, _P]),
     "hmse_debug_deflate_prof": (_I, [_PU64, _I]),
     "hmse_index_build": (_I, [_P, _P, _P, _U64, _P, _U64, _U64, _P, _U64, _P, _P, _P, _P]),
     "hmse_index_build_l4": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _U64, _P, _P, _P, _P, _P, _P, _P, _U64, _PU64, _P]),
@@ -77,6 +78,10 @@ SIGNATURES = {
     "hmse_chunk_sharded": (_I, [_P, _P, _P, _U64, _U64, _I, C.POINTER(CdcCfg), _P, _U64, _PU64, _PU64, _PU64, _PU64, _P]),
     "hmse_dedup_global": (_I, [_P, _P, _P, _U64, _U64, _P, _P, _P]),
     "hmse_lsh_exchange": (_I, [_P, _P, _P, _U64, _U32, _P, _U64, _PU64, _PU64, C.POINTER(_U32), _P]),
+    "hmse_alltoallv": (_I, [_P, _P, _P, _PU64, _P, _PU64, _U32, _U64, _P]),
+    "hmse_delta_heads": (_I, [_P, _P, _P, _P, _U64, _U32, _U64, _P, _P, _P]),
+    "hmse_delta_votes": (_I, [_P, _P, _U64, _U32, _U64, _U32, _I, _P, _P, _P, _P]),
+    "hmse_delta_encode_ext": (_I, [_P, _P, _U64, _P, _U64, _P, _P, _P, _U64, _P, _U64, _P, _PU64, _P]),
     "hmse_exchange_stats": (_I, [_P, _PU64, C.POINTER(_I)]),
     "hmse_corpus_lengths": (_I, [_P, C.POINTER(CorpusCfg), _P, _U64, _U64, _P, _P]),
     "hmse_corpus_render": (_I, [_P, C.POINTER(CorpusCfg), _P, _P, _U64, _U64, _P, _U64, _U64, _P, _P]),

@@ -200,6 +200,50 @@ class Context:
                                               C.byref(ib), C.byref(bo), self.stream))
         return owned[:nt.value * bo.value].view(nt.value, bo.value), ib.value
 
+    def allgather4(self, a: int, b: int = 0, c: int = 0, d: int = 0):
+        """[[a, b, c, d] of rank 0, ... of rank world-1] (hmse_allgather_u64: one collective, one host round trip)."""
+        w = self.comm_world
+        vals = (C.c_uint64 * 4)(int(a), int(b), int(c), int(d))
+        out = (C.c_uint64 * (4 * w))()
+        self.check(self.lib.hmse_allgather_u64(self.h, None, vals, out, self.stream))
+        return [[int(out[4 * r + q]) for q in range(4)] for r in range(w)]
+
+    def delta_heads(self, band: torch.Tensor, key: torch.Tensor, ids: torch.Tensor, n: int, bands: int) -> torch.Tensor:
+        """heads int32 [n, bands] (uint32 bit patterns): first id of every chunk's bucket, from sorted triples."""
+        heads = self.empty(max(1, n * bands), torch.int32)
+        self.check(self.lib.hmse_delta_heads(self.h, band.data_ptr(), key.data_ptr(), ids.data_ptr(), n, bands, 0, None,
+                                             heads.data_ptr(), self.stream))
+        return heads[:n * bands].view(n, bands)
+
+    def delta_votes(self, heads: torch.Tensor, id_base: int, min_votes: int, root_all: Optional[torch.Tensor] = None):
+        """pass 0 (root_all None): root flags uint8[n] of this rank's chunks; pass 1: base int64[n] (ids in the heads' space)."""
+        n, bands = int(heads.shape[0]), int(heads.shape[1])
+        heads = heads.contiguous()
+        if root_all is None:
+            root = self.empty(max(1, n), torch.uint8)
+            self.check(self.lib.hmse_delta_votes(self.h, heads.data_ptr(), n, bands, id_base, min_votes, 0, root.data_ptr(), None,
+                                                 None, self.stream))
+            return root[:n]
+        base = self.empty(max(1, n), torch.int64)
+        self.check(self.lib.hmse_delta_votes(self.h, heads.data_ptr(), n, bands, id_base, min_votes, 1, None, root_all.data_ptr(),
+                                             base.data_ptr(), self.stream))
+        return base[:n]
+
+    def alltoallv(self, send: torch.Tensor, send_counts, elem_bytes: int):
+        """(recv uint8 tensor, recv_counts list): `send` (uint8, elements of elem_bytes grouped by destination rank,
+        send_counts[world] of them per rank) through hmse_alltoallv."""
+        w = self.comm_world
+        sc = (C.c_uint64 * w)(*[int(c) for c in send_counts])
+        rc = (C.c_uint64 * w)()
+        send = send.contiguous()
+        self.check(self.lib.hmse_alltoallv(self.h, None, send.data_ptr() if send.numel() else None, sc, None, rc, elem_bytes, 0,
+                                           self.stream))
+        total = sum(int(x) for x in rc)
+        recv = self.empty(total * elem_bytes + _PAD, torch.uint8)     # slack: receivers may read whole words past the end
+        self.check(self.lib.hmse_alltoallv(self.h, None, send.data_ptr() if send.numel() else None, sc, recv.data_ptr(), rc,
+                                           elem_bytes, total, self.stream))
+        return recv[:total * elem_bytes], [int(x) for x in rc]
+
     def exchange_stats(self):
         """{bytes_sent, bytes_received, owned, contributed, rounds, ms} of the last exchange (ms only with hmse_timing on)."""
         out = (C.c_uint64 * 4)()
@@ -231,26 +275,22 @@ class Context:
         tensor of the required size is allocated (input bytes + per-chunk slack bounds any stream)."""
         m = cuts.numel() if select is None else select.numel()
         offsets = self.empty(m + 1, torch.int64)
-        if out is not None:
-            out_cap = out.numel()
-        elif out_cap is None:
-            out_cap = int(d.numel()) + 64 * m + 1024
         total = C.c_uint64(0)
         zp = zdict.data_ptr() if zdict is not None and zdict.numel() else None
         zl = zdict.numel() if zdict is not None else 0
         sp = select.data_ptr() if select is not None else None
-        for _ in range(2):
-            if out is None:
-                out = self.empty(out_cap, torch.uint8)
-            rc = self.lib.hmse_compress(self.h, d.data_ptr(), start0, cuts.data_ptr(), sp, m, zp, zl, level,
-                                        out.data_ptr(), out_cap, offsets.data_ptr(), C.byref(total), self.stream)
-            if rc == _lib.HMSE_E_CAPACITY and total.value > out_cap:
-                out_cap = int(total.value)
-                out = None
-                continue
-            self.check(rc)
-            return out[:total.value], offsets
-        raise HmseError(_lib.HMSE_E_CAPACITY, "hmse_compress: capacity retry failed")
+        cap = out.numel() if out is not None else (int(out_cap) if out_cap is not None else 0)
+        if out is None and cap:
+            out = self.empty(cap, torch.uint8)
+        # without a buffer the first call only sizes the result (the streams stay staged in the ctx) and the pack
+        # writes a blob of exactly that size; a buffer that turns out too small is replaced the same way
+        rc = self.lib.hmse_compress(self.h, d.data_ptr(), start0, cuts.data_ptr(), sp, m, zp, zl, level,
+                                    out.data_ptr() if out is not None else None, cap, offsets.data_ptr(), C.byref(total), self.stream)
+        if (out is None and rc == 0) or (rc == _lib.HMSE_E_CAPACITY and total.value > cap):
+            out = self.empty(max(1, total.value), torch.uint8)
+            rc = self.lib.hmse_compress_pack(self.h, offsets.data_ptr(), m, out.data_ptr(), out.numel(), self.stream)
+        self.check(rc)
+        return out[:total.value], offsets
 
     def inflate(self, blob: torch.Tensor, offsets: torch.Tensor, out_offsets: torch.Tensor, zdict: Optional[torch.Tensor]):
         """(out uint8[out_offsets[-1]], status int32[m], n_bad): every stream inflated on the device."""
@@ -306,9 +346,12 @@ class Context:
                                              f.contiguous().data_ptr(), min_votes, base.data_ptr(), self.stream))
         return base
 
-    def delta_encode(self, d: torch.Tensor, cuts: torch.Tensor, base: torch.Tensor, start0: int = 0):
-        """(blob, offsets int64[n+1]); `base` is updated in place (-1 where the 20 % rule rejected the delta)."""
+    def delta_encode(self, d: torch.Tensor, cuts: torch.Tensor, base: torch.Tensor, start0: int = 0, ext=None):
+        """(blob, offsets int64[n+1]); `base` is updated in place (-1 where the 20 % rule rejected the delta).
+        ext = (ext_data uint8 with slack, ext_off int64[n_ext + 1]): base values >= n name external bases (chunks of
+        another shard), see hmse_delta_encode_ext."""
         n = cuts.numel()
+        ep, eo, ne = (ext[0].data_ptr(), ext[1].data_ptr(), ext[1].numel() - 1) if ext is not None else (None, None, 0)
         offsets = self.empty(n + 1, torch.int64)
         total = C.c_uint64(0)
         # kept deltas are a fraction of a percent of the stream (0.14 % on the wiki corpus): 1/64 of it rarely needs the
@@ -316,8 +359,8 @@ class Context:
         out_cap = max(1 << 20, int(d.numel()) // 64)
         for _ in range(2):
             out = self.empty(out_cap + _PAD, torch.uint8)
-            rc = self.lib.hmse_delta_encode(self.h, d.data_ptr(), start0, cuts.data_ptr(), n, base.data_ptr(),
-                                            out.data_ptr(), out_cap, offsets.data_ptr(), C.byref(total), self.stream)
+            rc = self.lib.hmse_delta_encode_ext(self.h, d.data_ptr(), start0, cuts.data_ptr(), n, base.data_ptr(), ep, eo, ne,
+                                                out.data_ptr(), out_cap, offsets.data_ptr(), C.byref(total), self.stream)
             if rc == _lib.HMSE_E_CAPACITY and total.value > out_cap:
                 out_cap = int(total.value)  # the encode is deterministic: the retry reproduces it
                 continue

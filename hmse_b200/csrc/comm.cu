@@ -370,6 +370,56 @@ HMSE_API int hmse_lsh_exchange(hmse_ctx* ctx, void* comm, const uint64_t* d_keys
     return HMSE_OK;
 }
 
+HMSE_API int hmse_alltoallv(hmse_ctx* ctx, void* comm, const void* d_send, const uint64_t* send_counts, void* d_recv,
+                            uint64_t* recv_counts, uint32_t elem_bytes, uint64_t recv_cap, void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    Comm cm;
+    if (int rc = get_comm(ctx, comm, &cm)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!send_counts || !recv_counts || elem_bytes == 0) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_alltoallv: null counts / zero element size");
+    const int W = cm.world;
+    // counts first: matrix[r][o] = elements rank r sends to rank o (one all-gather, one mailbox read)
+    HMSE_SCRATCH(ctx, small, uint64_t*, SLOT_COMM_SMALL, (size_t)(W + 1) * (size_t)W * 8 + 64);
+    for (int p = 0; p < W; p++) ctx->pinned[1024 + p] = send_counts[p];   // staged through the mapped mailbox (upper half)
+    HMSE_CUDA(ctx, cudaMemcpyAsync(small, ctx->pinned_dev + 1024, (size_t)W * 8, cudaMemcpyDefault, st));
+    HT_BEGIN(ctx, HT_EXCHANGE, st);
+    HMSE_NCCL(ctx, cm.api, cm.api->AllGather(small, small + W, (size_t)W, ncclUint64, cm.comm, st));
+    if (int rc = hmse_mail(ctx, 0, small + W, (uint32_t)(W * W * 2), st)) return rc;
+    HMSE_CUDA(ctx, cudaStreamSynchronize(st));
+    uint64_t soff = 0, roff = 0, total_r = 0, total_s = 0;
+    for (int p = 0; p < W; p++) {
+        recv_counts[p] = ctx->pinned[(size_t)p * W + cm.rank];
+        total_r += recv_counts[p];
+        total_s += send_counts[p];
+    }
+    if (total_r > recv_cap || (total_r && !d_recv) || (total_s && !d_send)) {
+        HT_END(ctx, HT_EXCHANGE, st);
+        if (!d_recv && recv_cap == 0) return HMSE_OK;   // counts only
+        HMSE_FAIL(ctx, HMSE_E_CAPACITY, "hmse_alltoallv: d_recv holds %llu elements, %llu arrive", (unsigned long long)recv_cap,
+                  (unsigned long long)total_r);
+    }
+    uint64_t sent = 0, got = 0;
+    HMSE_NCCL(ctx, cm.api, cm.api->GroupStart());
+    for (int p = 0; p < W; p++) {
+        const uint64_t sb = send_counts[p] * elem_bytes, rb = recv_counts[p] * elem_bytes;
+        if (sb) HMSE_NCCL(ctx, cm.api, cm.api->Send((const uint8_t*)d_send + soff, sb, ncclUint8, p, cm.comm, st));
+        if (rb) HMSE_NCCL(ctx, cm.api, cm.api->Recv((uint8_t*)d_recv + roff, rb, ncclUint8, p, cm.comm, st));
+        soff += sb;
+        roff += rb;
+        if (p != cm.rank) {
+            sent += sb;
+            got += rb;
+        }
+    }
+    HMSE_NCCL(ctx, cm.api, cm.api->GroupEnd());
+    HT_END(ctx, HT_EXCHANGE, st);
+    ctx->comm_stat[0] = sent;
+    ctx->comm_stat[1] = got;
+    ctx->comm_stat[2] = total_r;
+    ctx->comm_stat[3] = total_s;
+    return HMSE_OK;
+}
+
 HMSE_API int hmse_exchange_stats(hmse_ctx* ctx, uint64_t* out4, int* rounds) {
     if (!ctx || !out4) return HMSE_E_INVAL;
     for (int i = 0; i < 4; i++) out4[i] = ctx->comm_stat[i];

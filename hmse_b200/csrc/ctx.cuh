@@ -77,6 +77,8 @@ struct hmse_ctx {
     uint64_t stat[4];  // [0] parse launches, [1] token words written, [2] input bytes parsed, [3] chunks parsed
     uint64_t dedup_cap, dedup_n;  // streaming dedup table (hmse_dedup_begin / hmse_dedup_append)
     void* dict_host;  // host copy + checksum of the indexed preset dictionary (deflate.cu)
+    uint64_t pack_m, pack_total;  // streams / bytes staged by the last hmse_compress, still waiting in SLOT_DEFLATE_STAGE
+    int pack_valid;               // (hmse_compress_pack copies them out without compressing again)
     // multi-GPU (comm.cu)
     void* comm;       // ncclComm_t made by hmse_comm_init (null: callers pass their own)
     int comm_owned;

@@ -1755,6 +1755,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     cudaStream_t st = (cudaStream_t)stream;
     if (!total || !d_offsets) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_compress: total/d_offsets is null");
     *total = 0;
+    ctx->pack_valid = 0;
     if (dict_len > DICT_MAX) HMSE_FAIL(ctx, HMSE_E_INVAL, "dict_len must be <= 32768");
     if (dict_len && !d_zdict) HMSE_FAIL(ctx, HMSE_E_INVAL, "d_zdict is null");
     if (level != 0 && level != 6)
@@ -1763,6 +1764,8 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     if (m >= 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "too many chunks in one call");
     if (m == 0) {
         HMSE_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, 8, st));
+        ctx->pack_m = ctx->pack_total = 0;
+        ctx->pack_valid = 1;
         return HMSE_OK;
     }
     if (!d_data || !d_cuts) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_compress: null pointer");
@@ -2021,9 +2024,32 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     ctx->stat[1] = mail[4];
     ctx->stat[2] = mail[5];
     ctx->stat[3] = mail[6];
+    // the streams now sit in the stage slots; they stay there until the next hmse_compress on this ctx, so a caller
+    // that did not know the size (d_out == NULL) or guessed too small packs them with hmse_compress_pack - no recompression
+    ctx->pack_m = m;
+    ctx->pack_total = mail[0];
+    ctx->pack_valid = 1;
+    if (!d_out && out_cap == 0) return HMSE_OK;   // sizes only
     if (!d_out || mail[0] > out_cap)
         HMSE_FAIL(ctx, HMSE_E_CAPACITY, "d_out capacity %llu < %llu bytes", (unsigned long long)out_cap,
                   (unsigned long long)mail[0]);
+    return hmse_compress_pack(ctx, d_offsets, m, d_out, out_cap, stream);
+}
+
+HMSE_API int hmse_compress_pack(hmse_ctx* ctx, const uint64_t* d_offsets, uint64_t m, uint8_t* d_out, uint64_t out_cap,
+                                void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->pack_valid || m != ctx->pack_m)
+        HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_compress_pack: no staged result of %llu streams (call hmse_compress first)",
+                  (unsigned long long)m);
+    if (m == 0) return HMSE_OK;
+    if (!d_offsets || !d_out) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_compress_pack: null pointer");
+    if (ctx->pack_total > out_cap)
+        HMSE_FAIL(ctx, HMSE_E_CAPACITY, "d_out capacity %llu < %llu bytes", (unsigned long long)out_cap,
+                  (unsigned long long)ctx->pack_total);
+    const uint8_t* stage = (const uint8_t*)ctx->slot[SLOT_DEFLATE_STAGE];
+    const uint64_t* slot_off = (const uint64_t*)ctx->slot[SLOT_DEFLATE_MISC] + m;   // [slot_size m][slot_off m] ...
     const uint64_t pg = m < (uint64_t)ctx->sm_count * 16 ? m : (uint64_t)ctx->sm_count * 16;
     HT_BEGIN(ctx, HT_PACK, st);
     KL(ctx);

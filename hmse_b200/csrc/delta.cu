@@ -49,28 +49,32 @@ __global__ void heads_kernel(const uint32_t* __restrict__ band, const uint64_t* 
     // the bucket (in one stream a duplicate is preceded by its first occurrence, so this loop does not run; it does on
     // a shard whose duplicates have their first occurrence elsewhere).  No first occurrence at all: the chunk itself.
     int64_t hd = start;
-    while (hd < t && !is_first[id[hd] - id_base]) hd++;
+    if (is_first)
+        while (hd < t && !is_first[id[hd] - id_base]) hd++;
     heads[(id[t] - id_base) * bands + b] = (uint32_t)(id[hd] - id_base);
 }
 
-// pass 0: root flags; pass 1: bases.  One warp per chunk, one lane per band (bands <= 32).
+// pass 0: root flags; pass 1: bases.  One warp per chunk, one lane per band (bands <= 32).  Chunk i of this call has id
+// id_base + i and `heads` hold ids in the same space (single GPU: id_base 0; sharded: global ids of the first occurrences
+// of the whole stream, where root_in covers ALL of them and root_out only this rank's).
 template <int PASS>
 __global__ void __launch_bounds__(256) votes_kernel(const uint32_t* __restrict__ heads, uint64_t n, uint32_t bands,
-                                                    const uint8_t* __restrict__ is_first, uint32_t min_votes,
-                                                    uint8_t* __restrict__ root, int64_t* __restrict__ base) {
+                                                    const uint8_t* __restrict__ is_first, uint32_t min_votes, uint64_t id_base,
+                                                    uint8_t* __restrict__ root_out, const uint8_t* __restrict__ root_in,
+                                                    int64_t* __restrict__ base) {
     const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (i >= n) return;
-    const bool first = is_first[i] != 0;
+    const bool first = is_first ? is_first[i] != 0 : true;
     const uint32_t h = lane < bands ? heads[i * bands + lane] : 0xFFFFFFFFu;  // idle lanes: a value no chunk has
-    const bool earlier = (uint64_t)h < i;
+    const bool earlier = (uint64_t)h < id_base + i;
     uint32_t votes = __popc(__match_any_sync(0xFFFFFFFFu, h));
     if (!earlier) votes = 0;
     if (PASS == 0) {
         const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, votes);
-        if (lane == 0) root[i] = first && best < min_votes;
+        if (lane == 0) root_out[i] = first && best < min_votes;
     } else {
-        const bool ok = earlier && votes >= min_votes && root[earlier ? h : 0];
+        const bool ok = earlier && votes >= min_votes && root_in[earlier ? h : 0];
         // most votes, then the smaller id
         const unsigned long long score = ok ? ((unsigned long long)votes << 32) | (0xFFFFFFFFu - h) : 0ull;
         unsigned long long best = score;
@@ -104,7 +108,10 @@ __device__ __forceinline__ uint8_t* put_varint(uint8_t* o, uint32_t v) {
 
 // cap[i] = floor(len/5) for chunks that have a candidate base and fit the size limits, else 0; candidates are
 // appended to `list` (processing order does not influence any output).
+// A base index j >= n names external base j - n: ext_data[ext_off[j - n] : ext_off[j - n + 1]) (a chunk of another shard,
+// fetched before the call); external bases precede their targets in the stream by construction.
 __global__ void delta_plan_kernel(uint64_t start0, const uint64_t* __restrict__ cuts, uint64_t n, int64_t* __restrict__ base,
+                                  const uint64_t* __restrict__ ext_off, uint64_t n_ext,
                                   uint64_t* __restrict__ cap, uint32_t* __restrict__ list, uint32_t* __restrict__ n_list) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -112,8 +119,11 @@ __global__ void delta_plan_kernel(uint64_t start0, const uint64_t* __restrict__ 
     const int64_t j = base[i];
     if (j >= 0) {
         const uint64_t len = cuts[i] - (i ? cuts[i - 1] : start0);
-        const uint64_t bl = cuts[j] - (j ? cuts[j - 1] : start0);
-        if ((uint64_t)j < i && len <= DELTA_MAX && bl <= DELTA_MAX && len >= 5) {
+        const bool ext = (uint64_t)j >= n;
+        uint64_t bl = DELTA_MAX + 1;
+        if (!ext) bl = cuts[j] - (j ? cuts[j - 1] : start0);
+        else if ((uint64_t)j - n < n_ext) bl = ext_off[j - n + 1] - ext_off[j - n];
+        if ((ext || (uint64_t)j < i) && len <= DELTA_MAX && bl <= DELTA_MAX && len >= 5) {
             c = len / 5;
             list[atomicAdd(n_list, 1u)] = (uint32_t)i;
         } else {
@@ -133,6 +143,9 @@ struct EncArgs {
     const uint64_t* slot;  // exclusive scan of cap
     uint8_t* stage;
     uint64_t* size;        // bytes of the kept delta (0: none)
+    uint64_t n;            // chunks of this call: base indices >= n are external
+    const uint8_t* ext_data;
+    const uint64_t* ext_off;
 };
 
 __global__ void __launch_bounds__(DT) delta_encode_kernel(EncArgs a) {
@@ -144,10 +157,19 @@ __global__ void __launch_bounds__(DT) delta_encode_kernel(EncArgs a) {
     for (uint32_t w = blockIdx.x; w < n_list; w += gridDim.x) {
         const uint64_t i = a.list[w];
         const uint64_t j = (uint64_t)a.base[i];
-        const uint64_t t0 = i ? a.cuts[i - 1] : a.start0, b0 = j ? a.cuts[j - 1] : a.start0;
-        const uint32_t n = (uint32_t)(a.cuts[i] - t0), nb = (uint32_t)(a.cuts[j] - b0);
+        const uint64_t t0 = i ? a.cuts[i - 1] : a.start0;
+        const uint32_t n = (uint32_t)(a.cuts[i] - t0);
         const uint8_t* T = a.data + t0;
-        const uint8_t* B = a.data + b0;
+        const uint8_t* B;
+        uint32_t nb;
+        if (j >= a.n) {
+            B = a.ext_data + a.ext_off[j - a.n];
+            nb = (uint32_t)(a.ext_off[j - a.n + 1] - a.ext_off[j - a.n]);
+        } else {
+            const uint64_t b0 = j ? a.cuts[j - 1] : a.start0;
+            B = a.data + b0;
+            nb = (uint32_t)(a.cuts[j] - b0);
+        }
         __syncthreads();  // the previous pair's walk is done with H / seedbits
         for (uint32_t k = tid; k < (1u << DHB); k += DT) H[k] = DEMPTY;
         __syncthreads();
@@ -352,9 +374,9 @@ HMSE_API int hmse_delta_bases(hmse_ctx* ctx, const uint32_t* d_band, const uint6
     heads_kernel<<<(unsigned)div_up64(n * bands, 256), 256, 0, st>>>(d_band, d_key, d_id, n * bands, bands, id_base, d_is_first,
                                                                      heads);
     KL(ctx);
-    votes_kernel<0><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(heads, n, bands, d_is_first, min_votes, root, d_base);
+    votes_kernel<0><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(heads, n, bands, d_is_first, min_votes, 0, root, root, d_base);
     KL(ctx);
-    votes_kernel<1><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(heads, n, bands, d_is_first, min_votes, root, d_base);
+    votes_kernel<1><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(heads, n, bands, d_is_first, min_votes, 0, root, root, d_base);
     HMSE_LAUNCH_CHECK(ctx);
     HT_END(ctx, HT_DELTA, st);
     return HMSE_OK;
@@ -363,7 +385,49 @@ HMSE_API int hmse_delta_bases(hmse_ctx* ctx, const uint32_t* d_band, const uint6
 HMSE_API int hmse_delta_encode(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts, uint64_t n,
                                int64_t* d_base, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total,
                                void* stream) {
+    return hmse_delta_encode_ext(ctx, d_data, start0, d_cuts, n, d_base, nullptr, nullptr, 0, d_out, out_cap, d_offsets, total, stream);
+}
+
+HMSE_API int hmse_delta_heads(hmse_ctx* ctx, const uint32_t* d_band, const uint64_t* d_key, const uint64_t* d_id, uint64_t n,
+                              uint32_t bands, uint64_t id_base, const uint8_t* d_is_first, uint32_t* d_heads, void* stream) {
     if (!ctx) return HMSE_E_INVAL;
+    if (n == 0 || bands == 0) return HMSE_OK;
+    if (!d_band || !d_key || !d_id || !d_heads) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_heads: null pointer");
+    if (n > 0xFFFFFFFEull) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_heads: n exceeds 2^32 - 2");
+    KL(ctx);
+    heads_kernel<<<(unsigned)div_up64(n * bands, 256), 256, 0, (cudaStream_t)stream>>>(d_band, d_key, d_id, n * bands, bands, id_base,
+                                                                                      d_is_first, d_heads);
+    HMSE_LAUNCH_CHECK(ctx);
+    return HMSE_OK;
+}
+
+HMSE_API int hmse_delta_votes(hmse_ctx* ctx, const uint32_t* d_heads, uint64_t n, uint32_t bands, uint64_t id_base,
+                              uint32_t min_votes, int pass, uint8_t* d_root_local, const uint8_t* d_root_all, int64_t* d_base,
+                              void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    if (n == 0) return HMSE_OK;
+    if (bands == 0 || bands > 32 || min_votes == 0) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_votes: bands must be 1..32, min_votes >= 1");
+    if (!d_heads || (pass == 0 && !d_root_local) || (pass == 1 && (!d_root_all || !d_base)) || (pass != 0 && pass != 1))
+        HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_votes: null pointer or bad pass");
+    if (id_base + n > 0xFFFFFFFEull) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_votes: ids exceed 2^32 - 2");
+    cudaStream_t st = (cudaStream_t)stream;
+    KL(ctx);
+    if (pass == 0)
+        votes_kernel<0><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(d_heads, n, bands, nullptr, min_votes, id_base, d_root_local,
+                                                                         nullptr, nullptr);
+    else
+        votes_kernel<1><<<(unsigned)div_up64(n * 32, 256), 256, 0, st>>>(d_heads, n, bands, nullptr, min_votes, id_base, nullptr,
+                                                                         d_root_all, d_base);
+    HMSE_LAUNCH_CHECK(ctx);
+    return HMSE_OK;
+}
+
+HMSE_API int hmse_delta_encode_ext(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts, uint64_t n,
+                                   int64_t* d_base, const uint8_t* d_ext_data, const uint64_t* d_ext_off, uint64_t n_ext,
+                                   uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total, void* stream) {
+    if (!ctx) return HMSE_E_INVAL;
+    if (n_ext && (!d_ext_data || !d_ext_off)) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_encode_ext: null external bases");
+    if (n_ext && ((uintptr_t)d_ext_data & 7)) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_encode_ext: d_ext_data must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (total) *total = 0;
     if (!d_offsets) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_delta_encode: null d_offsets");
@@ -384,7 +448,7 @@ HMSE_API int hmse_delta_encode(hmse_ctx* ctx, const uint8_t* d_data, uint64_t st
     HMSE_CUDA(ctx, cudaMemsetAsync(n_list, 0, 4, st));
     HMSE_CUDA(ctx, cudaMemsetAsync(size, 0, (n + 1) * 8, st));
     KL(ctx);
-    delta_plan_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(start0, d_cuts, n, d_base, slot, list, n_list);
+    delta_plan_kernel<<<(unsigned)div_up64(n, 256), 256, 0, st>>>(start0, d_cuts, n, d_base, d_ext_off, n_ext, slot, list, n_list);
     HMSE_LAUNCH_CHECK(ctx);
     if (int rc = hmse_exclusive_scan_u64(ctx, slot, slot, n, slot + n, st)) return rc;
     if (int rc = hmse_mail(ctx, 0, slot + n, 2, st)) return rc;
@@ -394,7 +458,7 @@ HMSE_API int hmse_delta_encode(hmse_ctx* ctx, const uint8_t* d_data, uint64_t st
     const uint32_t cands = (uint32_t)ctx->pinned[1];
     if (cands) {
         HMSE_SCRATCH(ctx, stage, uint8_t*, SLOT_DELTA_STAGE, stage_bytes + 16);
-        EncArgs ea{d_data, start0, d_cuts, d_base, list, n_list, slot, stage, size};
+        EncArgs ea{d_data, start0, d_cuts, d_base, list, n_list, slot, stage, size, n, d_ext_data, d_ext_off};
         const uint32_t grid = cands < (uint32_t)ctx->sm_count * 3 ? cands : (uint32_t)ctx->sm_count * 3;
         const size_t smem = ((1u << DHB) + DELTA_MAX / 32) * 4;
         HMSE_CUDA(ctx, cudaFuncSetAttribute(delta_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

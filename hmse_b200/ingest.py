@@ -444,14 +444,18 @@ class ShardedIngest(Ingest):
         self._s_in = None
         self._stage = [None, None]
         self._in = [None, None]
+        self.trace = None      # set to a list: run_batches appends CUDA-event tuples per batch (bench.py's timeline)
+        self.last_l4 = None
 
     def run(self, d: torch.Tensor, n_own: int, eof: bool, compress: bool = True, host=None, groups: int = 8,
             l4: Optional[SimConfig] = None, min_votes: int = 4):
         """One shard.  With `host` (pinned buffers from host_buffers()) the results are left in host memory and the
         compressed blob leaves the device in `groups` pieces while the rest is still being compressed.
-        l4 (device results only): the similarity layer runs SHARD-LOCALLY on the chunks that are first occurrences in
-        the whole stream - `base` holds local chunk indices and bases never live on another GPU (near duplicates
-        whose original sits in another shard are stored whole); chunks that keep a delta are not compressed."""
+        l4 (device results only): the similarity layer over the chunks that are first occurrences in the whole stream.
+        With the C transport the LSH index is GLOBAL (similarity_delta_global): `base` holds global chunk ids and a base
+        may live on another GPU - the result equals oracle.delta over the whole stream.  With the torch transport the
+        layer runs shard-locally (`base` = local chunk indices; near duplicates whose original sits in another shard
+        are stored whole).  Chunks that keep a delta are not compressed."""
         import torch.distributed as dist
         ctx = self.ctx
         dev = ctx.tdev
@@ -492,7 +496,13 @@ class ShardedIngest(Ingest):
         if l4 is not None and n:
             if host is not None:
                 raise ValueError("l4 is not available together with host result buffers")
-            base, dblob, doffs = self.similarity_delta(d, cuts, first.view(torch.bool), l4, min_votes, start0=entry)
+            if self.transport == "c":
+                # global LSH index: bases may live on another GPU; `base` then holds GLOBAL chunk ids
+                g = self.similarity_delta_global(d, cuts, first, entry, id_base, l4, min_votes)
+                base, dblob, doffs = g["base_gid"], g["delta_blob"], g["delta_offsets"]
+                self.last_l4 = g
+            else:
+                base, dblob, doffs = self.similarity_delta(d, cuts, first.view(torch.bool), l4, min_votes, start0=entry)
             stored = (first.view(torch.bool) & (base < 0)).view(torch.uint8)
         sel = self.select_first(stored)
         if host is not None:
@@ -503,6 +513,92 @@ class ShardedIngest(Ingest):
             blob, offs = ctx.empty(0, torch.uint8), ctx.empty(1, torch.int64).zero_()
         return IngestResult(cuts, digests, canon, first.view(torch.bool), sel, blob, offs, entry, id_base,
                             base=base, delta_blob=dblob, delta_offsets=doffs)
+
+    def similarity_delta_global(self, d: torch.Tensor, cuts: torch.Tensor, first_u8: torch.Tensor, entry: int, id_base: int,
+                                sim: SimConfig, min_votes: int = 4):
+        """The L4 layer over the WHOLE stream (README.md:1553-1570: the LSH index a chunk probes is global): the chunks that
+        are first occurrences anywhere are signed on their own rank, every band's keys go to the band's owner
+        (hmse_lsh_exchange), the owners sort their bands and take the bucket heads (hmse_delta_heads), the heads travel
+        back to the chunks' ranks, root flags are computed locally and gathered, bases are chosen among ALL roots, and the
+        bytes of bases that live on another GPU are fetched (<= 32 KiB each) before the delta coding.  Equal to
+        oracle.delta on the whole stream.  Returns a dict: base_gid int64[n] (GLOBAL chunk id of the base, -1 none),
+        delta_blob, delta_offsets int64[n+1], plus what the read path needs (base_loc, ext_data, ext_off, ext_gid)."""
+        ctx = self.ctx
+        W = ctx.comm_world
+        if not W:
+            raise RuntimeError("similarity_delta_global needs the C transport (ctx.comm_init)")
+        dev = ctx.tdev
+        n = cuts.numel()
+        sel = self.select_first(first_u8)
+        m = sel.numel()
+        keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim, start0=entry, select=sel), sim)            # [m, bands]
+        owned, ubase = ctx.lsh_exchange(keys)                                                    # [M, bo] rows in global order
+        M, bo = int(owned.shape[0]), int(owned.shape[1])
+        info = ctx.allgather4(m, id_base)
+        ms = [r[0] for r in info]
+        ubases = [sum(ms[:r]) for r in range(W)]
+        assert ubases[ctx.comm_rank] == ubase and sum(ms) == M
+        # owners: bucket heads of the owned bands over all M first occurrences, rows back to their ranks
+        if M and bo:
+            band, key, ids = ctx.lsh_buckets(owned.contiguous())
+            heads_o = ctx.delta_heads(band, key, ids, M, bo)
+            del band, key, ids
+        else:
+            heads_o = ctx.empty(0, torch.int32)
+        recv, _ = ctx.alltoallv(heads_o.contiguous().view(-1).view(torch.uint8), [ms[r] * bo for r in range(W)], 4)
+        heads = torch.empty(m, sim.bands, dtype=torch.int32, device=dev)
+        off = 0
+        for o in range(W):
+            cols = len(range(o, sim.bands, W))
+            if cols and m:
+                heads[:, o::W] = recv[off:off + m * cols * 4].view(torch.int32).view(m, cols)
+            off += m * cols * 4
+        # roots: local pass, flags of everybody (u order = rank order), then the bases among all roots
+        root_local = ctx.delta_votes(heads, ubase, min_votes)
+        root_all, _ = ctx.alltoallv(root_local.repeat(W), [m] * W, 1)
+        base_u = ctx.delta_votes(heads, ubase, min_votes, root_all=root_all)                    # global first-occurrence ids
+        has = base_u >= 0
+        local = has & (base_u >= ubase) & (base_u < ubase + m)
+        remote = has & ~local
+        base_loc = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        if m:
+            base_loc[sel[local]] = sel[(base_u[local] - ubase)]
+        # fetch the remote bases: ids to their owners, (length, global chunk id) and the bytes back
+        req = torch.unique(base_u[remote]) if m else base_u[:0]                                  # ascending = grouped by owner
+        ends = torch.tensor([ubases[r] + ms[r] for r in range(W)], dtype=torch.int64, device=dev)
+        own_r = torch.bucketize(req, ends, right=True)
+        cnt = torch.bincount(own_r, minlength=W).tolist() if req.numel() else [0] * W
+        got, gcnt = ctx.alltoallv(req.contiguous().view(torch.uint8), cnt, 8)
+        want_j = sel[(got[:sum(gcnt) * 8].view(torch.int64) - ubase)] if sum(gcnt) else sel[:0]   # my chunks others asked for
+        starts = torch.cat([torch.full((1,), entry, dtype=torch.int64, device=dev), cuts[:-1]])
+        lens = (cuts - starts)
+        meta = torch.stack([lens[want_j], want_j + id_base], 1).contiguous()
+        back, _ = ctx.alltoallv(meta.view(-1).view(torch.uint8), gcnt, 16)
+        back = back[:req.numel() * 16].view(torch.int64).view(-1, 2)                               # request order
+        ext_len, ext_gid = back[:, 0].contiguous(), back[:, 1].contiguous()
+        # the bytes: packed per requester in request order
+        out_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens[want_j], 0)])
+        packed = ctx.empty(int(out_off[-1]) + 64, torch.uint8)
+        if want_j.numel():
+            src_off = starts[want_j].contiguous()
+            ctx.check(ctx.lib.hmse_segment_copy(ctx.h, d.data_ptr(), src_off.data_ptr(), packed.data_ptr(), out_off.data_ptr(),
+                                                want_j.numel(), ctx.stream))
+        per_req, pos = [], 0
+        lw = lens[want_j]
+        for c in gcnt:
+            per_req.append(int(lw[pos:pos + c].sum()) if c else 0)
+            pos += c
+        ext_data, _ = ctx.alltoallv(packed[:int(out_off[-1])], per_req, 1)
+        ext_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(ext_len, 0)])
+        if m and req.numel():
+            base_loc[sel[remote]] = n + torch.searchsorted(req, base_u[remote])
+        ext_store = ctx.empty(int(ext_off[-1]) + 64, torch.uint8)
+        ext_store[:int(ext_off[-1])].copy_(ext_data[:int(ext_off[-1])])
+        dblob, doffs = ctx.delta_encode(d, cuts, base_loc, start0=entry, ext=(ext_store, ext_off) if req.numel() else None)
+        base_gid = torch.where(base_loc < 0, base_loc, torch.where(base_loc < n, base_loc + id_base,
+                               ext_gid[(base_loc - n).clamp(min=0)] if req.numel() else base_loc))
+        return dict(base_gid=base_gid, delta_blob=dblob, delta_offsets=doffs, base_loc=base_loc, ext_data=ext_store, ext_off=ext_off,
+                    ext_gid=ext_gid, n_remote=int(req.numel()), n_unique=m, exchange=ctx.exchange_stats())
 
     def run_batches(self, batches, n_own: int, eof: bool, host, groups: int = 8):
         """A sequence of shard buffers in pinned host memory (one per step of a continuous ingest): generator of
@@ -516,6 +612,7 @@ class ShardedIngest(Ingest):
         if self._s_in is None:
             self._s_in = torch.cuda.Stream(ctx.tdev)
         ready, free = [None, None], [None, None]
+        marks = [None, None]      # (copy-in start, end) events of the batch in each slot, when tracing
 
         def fetch(slot: int, hb: torch.Tensor) -> int:
             n = hb.numel()
@@ -525,9 +622,14 @@ class ShardedIngest(Ingest):
             if free[slot] is not None:
                 self._s_in.wait_event(free[slot])
             with torch.cuda.stream(self._s_in):
+                if self.trace is not None:
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(self._s_in)
                 self._in[slot][:n].copy_(hb.view(-1), non_blocking=True)
-                ready[slot] = torch.cuda.Event()
+                ready[slot] = torch.cuda.Event(enable_timing=self.trace is not None)
                 ready[slot].record(self._s_in)
+                if self.trace is not None:
+                    marks[slot] = (t0, ready[slot])
             return n
 
         it = iter(batches)
@@ -540,9 +642,14 @@ class ShardedIngest(Ingest):
             nxt = next(it, None)
             n_next = fetch(slot ^ 1, nxt) if nxt is not None else 0
             cur.wait_event(ready[slot])
+            if self.trace is not None:
+                c0 = torch.cuda.Event(enable_timing=True)
+                c0.record(cur)
             res = self.run(self._in[slot][:n_cur], n_own, eof, host=host, groups=groups)
-            free[slot] = torch.cuda.Event()
+            free[slot] = torch.cuda.Event(enable_timing=self.trace is not None)
             free[slot].record(cur)
+            if self.trace is not None:      # (copy-in start, copy-in end, pipeline start, everything incl. copy-out done)
+                self.trace.append((marks[slot][0], marks[slot][1], c0, free[slot]))
             res.h2d_bytes = n_cur
             yield res
             if nxt is None:

@@ -189,6 +189,13 @@ int hmse_dedup_global(hmse_ctx* ctx, void* comm, const uint8_t* d_digests, uint6
  * *n_total holds the rows needed. */
 int hmse_lsh_exchange(hmse_ctx* ctx, void* comm, const uint64_t* d_keys, uint64_t n, uint32_t bands, uint64_t* d_owned,
                       uint64_t owned_cap_rows, uint64_t* n_total, uint64_t* id_base, uint32_t* bands_owned, void* stream);
+/* Generic variable all-to-all on `stream`: the elements (elem_bytes each) of d_send are grouped by destination rank,
+ * send_counts[world] (host) of them per rank; recv_counts[world] (host, out) = elements arriving from each rank, stored in
+ * d_recv in rank order.  The counts travel first (one all-gather, one host round trip).  d_recv == NULL with
+ * recv_cap == 0 only fills recv_counts; on HMSE_E_CAPACITY recv_counts is valid.  Used by the cross-shard L4 steps
+ * (heads back to the chunks' ranks, root flags to everybody, base chunk requests and their bytes). */
+int hmse_alltoallv(hmse_ctx* ctx, void* comm, const void* d_send, const uint64_t* send_counts, void* d_recv,
+                   uint64_t* recv_counts, uint32_t elem_bytes, uint64_t recv_cap, void* stream);
 /* Facts about the last exchange on ctx: out4 = {bytes sent to other ranks, bytes received from other ranks, records
  * (or rows) owned after the exchange, records (rows) contributed}; *rounds = resync rounds of the last
  * hmse_chunk_sharded (may be null). */
@@ -203,11 +210,16 @@ uint64_t hmse_compress_bound(uint64_t len);
  * d_out in selection order; d_offsets[m+1] are the stream boundaries.  d_select[k] is a chunk
  * index (NULL = chunks 0..m-1).  dict_len <= 32768.  level: 6 (match search and lazy rule tuned against zlib
  * level 6) or 0 (stored blocks); anything else fails with HMSE_E_INVAL.  *total (host) = d_offsets[m].
- * On HMSE_E_CAPACITY *total holds the required out_cap. */
+ * d_out == NULL with out_cap == 0: everything but the final copy is done (sizes only, HMSE_OK).  On HMSE_E_CAPACITY
+ * *total holds the required out_cap.  In both cases the streams stay staged inside ctx until the next hmse_compress and
+ * hmse_compress_pack copies them out - the chunks are never compressed twice. */
 int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
                   const uint64_t* d_select, uint64_t m, const uint8_t* d_zdict, uint32_t dict_len,
                   int level, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total,
                   void* stream);
+
+/* Packs the m streams staged by the last hmse_compress on ctx (same d_offsets) into d_out[0 : total). */
+int hmse_compress_pack(hmse_ctx* ctx, const uint64_t* d_offsets, uint64_t m, uint8_t* d_out, uint64_t out_cap, void* stream);
 
 /* Diagnostic: cycles spent per encoder phase (thread 0 of each CTA, summed over chunks) since
  * the last reset; out16[15] = chunks encoded.  Host pointer. */
@@ -288,6 +300,23 @@ int hmse_lsh_buckets(hmse_ctx* ctx, const uint64_t* d_keys, uint64_t n, uint32_t
 int hmse_delta_bases(hmse_ctx* ctx, const uint32_t* d_band, const uint64_t* d_key, const uint64_t* d_id, uint64_t n,
                      uint32_t bands, uint64_t id_base, const uint8_t* d_is_first, uint32_t min_votes, int64_t* d_base,
                      void* stream);
+/* The pieces of hmse_delta_bases for a stream sharded over several GPUs (ids are then GLOBAL ids of the first
+ * occurrences of the whole stream, README.md:1556-1559 "probe LSH index -> return base chunk" is a global lookup):
+ * hmse_delta_heads: d_heads[(id - id_base) * bands + band] = first id of the bucket, over sorted triples of n chunks
+ *   (d_is_first may be null = every chunk is a first occurrence) - run by the band owners after hmse_lsh_exchange;
+ * hmse_delta_votes pass 0: d_root_local[i] = no earlier head of chunk id_base + i reaches min_votes;
+ *   pass 1: d_base[i] = best-voted earlier head h with d_root_all[h] set (an id in the heads' id space), or -1.
+ *   d_heads[n][bands] belongs to this rank's chunks; d_root_all covers every id (all ranks' pass-0 results gathered). */
+int hmse_delta_heads(hmse_ctx* ctx, const uint32_t* d_band, const uint64_t* d_key, const uint64_t* d_id, uint64_t n,
+                     uint32_t bands, uint64_t id_base, const uint8_t* d_is_first, uint32_t* d_heads, void* stream);
+int hmse_delta_votes(hmse_ctx* ctx, const uint32_t* d_heads, uint64_t n, uint32_t bands, uint64_t id_base, uint32_t min_votes,
+                     int pass, uint8_t* d_root_local, const uint8_t* d_root_all, int64_t* d_base, void* stream);
+/* hmse_delta_encode with bases that are not chunks of d_data: d_base[i] >= n names external base d_base[i] - n, the bytes
+ * d_ext_data[d_ext_off[e] : d_ext_off[e + 1]) (8-byte aligned buffer, 16 readable bytes after the last base) - chunks of
+ * another shard fetched beforehand.  Everything else as hmse_delta_encode. */
+int hmse_delta_encode_ext(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts, uint64_t n,
+                          int64_t* d_base, const uint8_t* d_ext_data, const uint64_t* d_ext_off, uint64_t n_ext,
+                          uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total, void* stream);
 /* For every chunk i with d_base[i] >= 0: the delta of chunk i against chunk d_base[i] (greedy walk over 8-byte
  * seeds of a 16384-bucket index of the base that keeps the smallest position per bucket; backward then forward
  * extension), kept iff 5 * bytes <= chunk length; otherwise d_base[i] is reset to -1.  The kept deltas are packed
