@@ -392,11 +392,18 @@ HMSE_API int hmse_alltoallv(hmse_ctx* ctx, void* comm, const void* d_send, const
         total_r += recv_counts[p];
         total_s += send_counts[p];
     }
-    if (total_r > recv_cap || (total_r && !d_recv) || (total_s && !d_send)) {
+    // The size query (d_recv == NULL, recv_cap == 0) is a collective of its own and ends here on EVERY rank, whatever the
+    // counts: a rank that happened to receive nothing must not go on to send while its peers return (it would wait for
+    // receives that are never posted).
+    if (!d_recv && recv_cap == 0) {
         HT_END(ctx, HT_EXCHANGE, st);
-        if (!d_recv && recv_cap == 0) return HMSE_OK;   // counts only
-        HMSE_FAIL(ctx, HMSE_E_CAPACITY, "hmse_alltoallv: d_recv holds %llu elements, %llu arrive", (unsigned long long)recv_cap,
-                  (unsigned long long)total_r);
+        return HMSE_OK;
+    }
+    if (total_r > recv_cap || (total_s && !d_send)) {
+        HT_END(ctx, HT_EXCHANGE, st);
+        HMSE_FAIL(ctx, HMSE_E_CAPACITY, "hmse_alltoallv: d_recv holds %llu elements, %llu arrive (every rank must size its buffer "
+                                        "from the query call: a rank that fails here leaves its peers waiting)",
+                  (unsigned long long)recv_cap, (unsigned long long)total_r);
     }
     uint64_t sent = 0, got = 0;
     HMSE_NCCL(ctx, cm.api, cm.api->GroupStart());

@@ -7,6 +7,8 @@
 // Full blocks are read as aligned 32-bit words and byte-permuted into big-endian order with one
 // PRMT each (the chunk start is byte-unaligned); only the last one or two blocks of a chunk take
 // the byte-wise padding path.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 namespace {
@@ -200,10 +202,28 @@ HMSE_API int hmse_digest(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, 
     if (n_chunks > 0xFFFFFFFFull) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_digest: n_chunks exceeds 2^32");
     // persistent lanes: enough warps to fill the machine, never more lanes than chunks
     uint64_t blocks = div_up64(n_chunks, SHA_THREADS);
-    const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
+    uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
+    // A batch that gives the lanes of a full machine fewer than ~3 chunks each (a piece of a stream: 2 GiB = 229 k chunks
+    // for 151 k lanes) ends when its longest chunks end, and a lane runs slower the more warps share its scheduler (the
+    // alu pipe issues one warp instruction per two cycles: 8 warps per scheduler = one round instruction per 16 cycles).
+    // Fewer, faster lanes with ~3 chunks each, longest first, finish such a batch sooner: the alu pipe stays saturated down
+    // to about two warps per scheduler.
+    {
+        static int per_sm_override = -1;   // HMSE_SHA_BLOCKS_PER_SM: experiments (tools/sha_pieces.py)
+        if (per_sm_override < 0) {
+            const char* e = getenv("HMSE_SHA_BLOCKS_PER_SM");
+            per_sm_override = e ? atoi(e) : 0;
+        }
+        if (per_sm_override > 0) max_blocks = (uint64_t)ctx->sm_count * (uint64_t)per_sm_override;
+        else {
+            uint64_t per_sm = div_up64(div_up64(n_chunks, 3), (uint64_t)ctx->sm_count * SHA_THREADS);
+            if (per_sm < 2) per_sm = 2;
+            if (per_sm < 8) max_blocks = (uint64_t)ctx->sm_count * per_sm;
+        }
+    }
     if (blocks > max_blocks) blocks = max_blocks;
     const uint64_t lanes = max_blocks * SHA_THREADS;
-    // between one and six chunks per lane the stream order leaves long chunks for the end: order them longest first
+    // up to six chunks per lane the stream order leaves long chunks for the end: order them longest first
     const bool lpt = n_chunks > lanes && n_chunks < 6 * lanes;
     // misc: [counter u64][class counters u32 x 64][order u32 n]
     HMSE_SCRATCH(ctx, counter, unsigned long long*, SLOT_SHA_MISC, 8 + 256 + (lpt ? n_chunks * 4 : 0) + 64);

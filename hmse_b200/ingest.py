@@ -420,6 +420,22 @@ class IngestStream(Ingest):
                                 h2d_bytes=n, d2h_bytes=d2h)
 
 
+class CFabric:
+    """The collectives of sharding.global_delta_bases served by the library (csrc/comm.cu) on ctx's own communicator."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.world, self.rank = ctx, ctx.comm_world, ctx.comm_rank
+
+    def allgather4(self, a, b=0, c=0, d=0):
+        return self.ctx.allgather4(a, b, c, d)
+
+    def lsh_exchange(self, keys):
+        return self.ctx.lsh_exchange(keys)
+
+    def alltoallv(self, send, send_counts, elem_bytes):
+        return self.ctx.alltoallv(send, send_counts, elem_bytes)
+
+
 class ShardedIngest(Ingest):
     """Rank r holds stream bytes [lo_r, hi_r + max_size) (the last rank up to the stream end).
     Chunks are owned by the shard they start in; global ids follow stream order."""
@@ -524,81 +540,46 @@ class ShardedIngest(Ingest):
         oracle.delta on the whole stream.  Returns a dict: base_gid int64[n] (GLOBAL chunk id of the base, -1 none),
         delta_blob, delta_offsets int64[n+1], plus what the read path needs (base_loc, ext_data, ext_off, ext_gid)."""
         ctx = self.ctx
-        W = ctx.comm_world
-        if not W:
+        if not ctx.comm_world:
             raise RuntimeError("similarity_delta_global needs the C transport (ctx.comm_init)")
         dev = ctx.tdev
         n = cuts.numel()
         sel = self.select_first(first_u8)
-        m = sel.numel()
         keys = ctx.lsh_keys(ctx.minhash(d, cuts, sim, start0=entry, select=sel), sim)            # [m, bands]
-        owned, ubase = ctx.lsh_exchange(keys)                                                    # [M, bo] rows in global order
-        M, bo = int(owned.shape[0]), int(owned.shape[1])
-        info = ctx.allgather4(m, id_base)
-        ms = [r[0] for r in info]
-        ubases = [sum(ms[:r]) for r in range(W)]
-        assert ubases[ctx.comm_rank] == ubase and sum(ms) == M
-        # owners: bucket heads of the owned bands over all M first occurrences, rows back to their ranks
-        if M and bo:
-            band, key, ids = ctx.lsh_buckets(owned.contiguous())
-            heads_o = ctx.delta_heads(band, key, ids, M, bo)
-            del band, key, ids
-        else:
-            heads_o = ctx.empty(0, torch.int32)
-        recv, _ = ctx.alltoallv(heads_o.contiguous().view(-1).view(torch.uint8), [ms[r] * bo for r in range(W)], 4)
-        heads = torch.empty(m, sim.bands, dtype=torch.int32, device=dev)
-        off = 0
-        for o in range(W):
-            cols = len(range(o, sim.bands, W))
-            if cols and m:
-                heads[:, o::W] = recv[off:off + m * cols * 4].view(torch.int32).view(m, cols)
-            off += m * cols * 4
-        # roots: local pass, flags of everybody (u order = rank order), then the bases among all roots
-        root_local = ctx.delta_votes(heads, ubase, min_votes)
-        root_all, _ = ctx.alltoallv(root_local.repeat(W), [m] * W, 1)
-        base_u = ctx.delta_votes(heads, ubase, min_votes, root_all=root_all)                    # global first-occurrence ids
-        has = base_u >= 0
-        local = has & (base_u >= ubase) & (base_u < ubase + m)
-        remote = has & ~local
-        base_loc = torch.full((n,), -1, dtype=torch.int64, device=dev)
-        if m:
-            base_loc[sel[local]] = sel[(base_u[local] - ubase)]
-        # fetch the remote bases: ids to their owners, (length, global chunk id) and the bytes back
-        req = torch.unique(base_u[remote]) if m else base_u[:0]                                  # ascending = grouped by owner
-        ends = torch.tensor([ubases[r] + ms[r] for r in range(W)], dtype=torch.int64, device=dev)
-        own_r = torch.bucketize(req, ends, right=True)
-        cnt = torch.bincount(own_r, minlength=W).tolist() if req.numel() else [0] * W
-        got, gcnt = ctx.alltoallv(req.contiguous().view(torch.uint8), cnt, 8)
-        want_j = sel[(got[:sum(gcnt) * 8].view(torch.int64) - ubase)] if sum(gcnt) else sel[:0]   # my chunks others asked for
         starts = torch.cat([torch.full((1,), entry, dtype=torch.int64, device=dev), cuts[:-1]])
-        lens = (cuts - starts)
-        meta = torch.stack([lens[want_j], want_j + id_base], 1).contiguous()
-        back, _ = ctx.alltoallv(meta.view(-1).view(torch.uint8), gcnt, 16)
-        back = back[:req.numel() * 16].view(torch.int64).view(-1, 2)                               # request order
-        ext_len, ext_gid = back[:, 0].contiguous(), back[:, 1].contiguous()
-        # the bytes: packed per requester in request order
-        out_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens[want_j], 0)])
-        packed = ctx.empty(int(out_off[-1]) + 64, torch.uint8)
-        if want_j.numel():
-            src_off = starts[want_j].contiguous()
-            ctx.check(ctx.lib.hmse_segment_copy(ctx.h, d.data_ptr(), src_off.data_ptr(), packed.data_ptr(), out_off.data_ptr(),
-                                                want_j.numel(), ctx.stream))
-        per_req, pos = [], 0
-        lw = lens[want_j]
-        for c in gcnt:
-            per_req.append(int(lw[pos:pos + c].sum()) if c else 0)
-            pos += c
-        ext_data, _ = ctx.alltoallv(packed[:int(out_off[-1])], per_req, 1)
-        ext_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(ext_len, 0)])
-        if m and req.numel():
-            base_loc[sel[remote]] = n + torch.searchsorted(req, base_u[remote])
-        ext_store = ctx.empty(int(ext_off[-1]) + 64, torch.uint8)
-        ext_store[:int(ext_off[-1])].copy_(ext_data[:int(ext_off[-1])])
-        dblob, doffs = ctx.delta_encode(d, cuts, base_loc, start0=entry, ext=(ext_store, ext_off) if req.numel() else None)
+        lens = cuts - starts
+
+        class Ops:
+            @staticmethod
+            def heads(owned):
+                band, key, ids = ctx.lsh_buckets(owned.contiguous())
+                return ctx.delta_heads(band, key, ids, int(owned.shape[0]), int(owned.shape[1]))
+
+            @staticmethod
+            def votes(heads, ubase, mv, root_all):
+                return ctx.delta_votes(heads, ubase, mv, root_all=root_all)
+
+            @staticmethod
+            def chunk_bytes(want_j):
+                lw = lens[want_j]
+                out_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lw, 0)])
+                packed = ctx.empty(int(out_off[-1]) + 64, torch.uint8)
+                if want_j.numel():
+                    src_off = starts[want_j].contiguous()
+                    ctx.check(ctx.lib.hmse_segment_copy(ctx.h, d.data_ptr(), src_off.data_ptr(), packed.data_ptr(),
+                                                        out_off.data_ptr(), want_j.numel(), ctx.stream))
+                return packed, lw
+
+        g = sharding.global_delta_bases(CFabric(ctx), Ops, keys, sel, n, id_base, sim.bands, min_votes)
+        base_loc, ext_off, ext_gid = g["base_loc"], g["ext_off"], g["ext_gid"]
+        n_ext = int(ext_gid.numel())
+        ext_store = ctx.empty(int(ext_off[-1]) + 64, torch.uint8)      # 8-byte aligned, slack behind the last base
+        ext_store[:int(ext_off[-1])].copy_(g["ext_data"][:int(ext_off[-1])])
+        dblob, doffs = ctx.delta_encode(d, cuts, base_loc, start0=entry, ext=(ext_store, ext_off) if n_ext else None)
         base_gid = torch.where(base_loc < 0, base_loc, torch.where(base_loc < n, base_loc + id_base,
-                               ext_gid[(base_loc - n).clamp(min=0)] if req.numel() else base_loc))
+                               ext_gid[(base_loc - n).clamp(min=0)] if n_ext else base_loc))
         return dict(base_gid=base_gid, delta_blob=dblob, delta_offsets=doffs, base_loc=base_loc, ext_data=ext_store, ext_off=ext_off,
-                    ext_gid=ext_gid, n_remote=int(req.numel()), n_unique=m, exchange=ctx.exchange_stats())
+                    ext_gid=ext_gid, n_remote=n_ext, n_unique=int(sel.numel()), exchange=ctx.exchange_stats())
 
     def run_batches(self, batches, n_own: int, eof: bool, host, groups: int = 8):
         """A sequence of shard buffers in pinned host memory (one per step of a continuous ingest): generator of

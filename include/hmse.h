@@ -192,7 +192,9 @@ int hmse_lsh_exchange(hmse_ctx* ctx, void* comm, const uint64_t* d_keys, uint64_
 /* Generic variable all-to-all on `stream`: the elements (elem_bytes each) of d_send are grouped by destination rank,
  * send_counts[world] (host) of them per rank; recv_counts[world] (host, out) = elements arriving from each rank, stored in
  * d_recv in rank order.  The counts travel first (one all-gather, one host round trip).  d_recv == NULL with
- * recv_cap == 0 only fills recv_counts; on HMSE_E_CAPACITY recv_counts is valid.  Used by the cross-shard L4 steps
+ * recv_cap == 0 is the size query: it only fills recv_counts and moves no data - a collective of its own that every
+ * rank must make; the exchange proper follows with buffers of at least those sizes (d_recv non-null even when nothing
+ * arrives).  Used by the cross-shard L4 steps
  * (heads back to the chunks' ranks, root flags to everybody, base chunk requests and their bytes). */
 int hmse_alltoallv(hmse_ctx* ctx, void* comm, const void* d_send, const uint64_t* send_counts, void* d_recv,
                    uint64_t* recv_counts, uint32_t elem_bytes, uint64_t recv_cap, void* stream);

@@ -143,3 +143,106 @@ def test_lsh_band_exchange_over_gloo(world):
     wb, wk, wi = om.buckets(keys)
     triples = sorted(zip(sum((g[1] for g in got), []), sum((g[2] for g in got), []), sum((g[3] for g in got), [])))
     assert triples == list(zip(wb.tolist(), wk.tolist(), wi.tolist()))
+
+
+def _votes_np(heads, ubase, min_votes, root_all):
+    """The votes rule of oracle/deltacode.py::delta_bases on given heads (ids in the global first-occurrence space):
+    pass 0 (root_all None) -> root flags of these chunks; pass 1 -> base id or -1."""
+    h = heads.numpy().astype(np.int64) & 0xFFFFFFFF
+    m = h.shape[0]
+    if root_all is None:
+        out = np.zeros(m, dtype=np.uint8)
+        for i in range(m):
+            js, cnt = np.unique(h[i][h[i] < ubase + i], return_counts=True)
+            out[i] = cnt.size == 0 or int(cnt.max()) < min_votes
+        return torch.from_numpy(out)
+    root = root_all.numpy().astype(bool)
+    base = np.full(m, -1, dtype=np.int64)
+    for i in range(m):
+        js, cnt = np.unique(h[i][h[i] < ubase + i], return_counts=True)
+        ok = root[js] & (cnt >= min_votes)
+        if ok.any():
+            js, cnt = js[ok], cnt[ok]
+            base[i] = int(js[np.argmax(cnt)])
+    return torch.from_numpy(base)
+
+
+def _l4_worker(rank, world, port, n_bytes, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from oracle import corpus
+        from hmse_b200 import sharding
+        data = corpus.generate(n_bytes)
+        cuts = oracle.chunk_c(data)
+        n_all = cuts.size
+        starts = np.concatenate([[0], cuts[:-1]]).astype(np.int64)
+        _, first = oracle.dedup(oracle.digest(data, cuts))
+        keys_all = oracle.band_keys(oracle.minhash_c(data, cuts))
+        bounds = np.linspace(0, n_all, world + 1).astype(int)       # the shard of a rank = a contiguous range of chunks
+        if world == 3:
+            bounds[2] = bounds[1]                                    # a rank without chunks
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        sel = np.flatnonzero(first[lo:hi])                           # local indices of the globally-first chunks
+        keys = torch.from_numpy(keys_all[lo:hi][sel].view(np.int64).copy()).view(-1, 32)
+
+        class Ops:
+            @staticmethod
+            def heads(owned):
+                return torch.from_numpy(oracle.lsh_heads(owned.numpy().view(np.uint64)).astype(np.int32))
+
+            @staticmethod
+            def votes(heads, ubase, mv, root_all):
+                return _votes_np(heads, ubase, mv, root_all)
+
+            @staticmethod
+            def chunk_bytes(want_j):
+                js = (want_j.numpy() + lo).tolist()
+                parts = [data[starts[j]:int(cuts[j])] for j in js]
+                lens = torch.tensor([p.size for p in parts], dtype=torch.int64)
+                blob = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+                return torch.from_numpy(blob.copy()), lens
+
+        g = sharding.global_delta_bases(sharding.TorchFabric(), Ops, keys, torch.from_numpy(sel.astype(np.int64)), hi - lo, lo, 32, 4)
+        bl = g["base_loc"].numpy()
+        n = hi - lo
+        ext_gid = g["ext_gid"].numpy()
+        gid = np.where(bl < 0, -1, np.where(bl < n, bl + lo, ext_gid[np.clip(bl - n, 0, max(0, ext_gid.size - 1))] if ext_gid.size else -1))
+        # the fetched bytes are the base chunks' bytes
+        eo = g["ext_off"].numpy()
+        ed = g["ext_data"].numpy()
+        for e, j in enumerate(ext_gid.tolist()):
+            assert ed[eo[e]:eo[e + 1]].tobytes() == data[starts[j]:int(cuts[j])].tobytes()
+        q.put((rank, gid.tolist(), int(ext_gid.size)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_global_l4_bases_over_gloo(world):
+    """sharding.global_delta_bases (the orchestration the GPU path runs over the C fabric) with torch.distributed / gloo
+    and the oracle as local compute: bases chosen through the owner-side bucket heads, the gathered root flags and the
+    remote-base fetch equal oracle.delta_bases over the whole stream, including bases that live on another rank."""
+    import oracle
+    from oracle import corpus
+    n_bytes = 5 << 19
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_l4_worker, args=(r, world, port, n_bytes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    data = corpus.generate(n_bytes)
+    cuts = oracle.chunk_c(data)
+    _, first = oracle.dedup(oracle.digest(data, cuts))
+    keys_all = oracle.band_keys(oracle.minhash_c(data, cuts))
+    want = oracle.delta_bases(keys_all, first)
+    base = np.array(sum((g[1] for g in got), []), dtype=np.int64)
+    assert np.array_equal(base, want)
+    assert (want >= 0).sum() >= 5 and sum(g[2] for g in got) >= 1      # some bases crossed a rank boundary
