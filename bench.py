@@ -549,8 +549,9 @@ def run_ours(args):
             is_ext = bl_ >= n_chunks
             both = torch.cat([d, g["ext_data"]])
             e_ = (bl_ - n_chunks).clamp(min=0)
-            bo = torch.where(is_ext, d.numel() + g["ext_off"][e_], starts[bl_.clamp(max=n_chunks - 1)]).contiguous()
-            bl = torch.where(is_ext, g["ext_off"][e_ + 1] - g["ext_off"][e_], lens[bl_.clamp(max=n_chunks - 1)]).to(torch.int32).contiguous()
+            eo_ = torch.cat([g["ext_off"], g["ext_off"][-1:]])    # (torch.where evaluates both sides: keep e_ + 1 in range)
+            bo = torch.where(is_ext, d.numel() + eo_[e_], starts[bl_.clamp(max=n_chunks - 1)]).contiguous()
+            bl = torch.where(is_ext, eo_[e_ + 1] - eo_[e_], lens[bl_.clamp(max=n_chunks - 1)]).to(torch.int32).contiguous()
             out_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(lens[kept], 0)])
             doff_k = torch.cat([g["delta_offsets"][kept], g["delta_offsets"][-1:]])
             rebuilt, dstatus, dbad = ctx.delta_apply(g["delta_blob"], doff_k, both, bo, bl, out_off)

@@ -38,6 +38,7 @@ SIGNATURES = {
     "hmse_destroy": (None, [_P]),
     "hmse_last_error": (C.c_char_p, [_P]),
     "hmse_scratch_bytes": (_U64, [_P]),
+    "hmse_guard_check": (_I, [_P]),
     "hmse_chunk": (_I, [_P, _P, _U64, C.POINTER(CdcCfg), _P, _U64, _PU64, _P]),
     "hmse_chunk_scan": (_I, [_P, _P, _U64, C.POINTER(CdcCfg), _P]),
     "hmse_chunk_resolve": (_I, [_P, _P, _U64, _U64, _I, _U64, _P, _U64, _PU64, _PU64, _P]),

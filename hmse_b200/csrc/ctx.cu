@@ -47,7 +47,7 @@ HMSE_API void hmse_destroy(hmse_ctx* ctx) {
     cudaSetDevice(ctx->device);
     hmse_comm_destroy(ctx);
     for (int i = 0; i < SLOT_COUNT; i++)
-        if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+        if (ctx->slot[i]) cudaFree(ctx->slot_base[i]);
     for (int i = 0; i < 2 * HT_COUNT; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 2 * HMSE_PARSE_EVENTS; i++)
@@ -66,22 +66,37 @@ HMSE_API uint64_t hmse_scratch_bytes(hmse_ctx* ctx) {
     return s;
 }
 
+// HMSE_GUARD=1 (checked mode of the test suite; compute-sanitizer is closed on the B200 pool): every scratch slot is
+// surrounded by two 4 KiB bands of 0xA5 that hmse_guard_check compares - a kernel that writes outside its scratch slot is
+// caught at the end of the test that ran it.
+constexpr size_t GUARD_BYTES = 4096;
+static int guard_mode() {
+    static int g = -1;
+    if (g < 0) {
+        const char* e = getenv("HMSE_GUARD");
+        g = (e && *e && *e != '0') ? 1 : 0;
+    }
+    return g;
+}
+
 void* hmse_scratch(hmse_ctx* ctx, int slot, size_t bytes) {
     if (bytes == 0) bytes = 256;
     if (ctx->slot_bytes[slot] >= bytes) return ctx->slot[slot];
     if (ctx->slot[slot]) {
-        cudaFree(ctx->slot[slot]);
-        ctx->slot[slot] = nullptr;
+        cudaFree(ctx->slot_base[slot]);
+        ctx->slot[slot] = ctx->slot_base[slot] = nullptr;
         ctx->slot_bytes[slot] = 0;
     }
-    size_t want = bytes + bytes / 8;  // headroom so slowly growing inputs do not thrash
+    const size_t G = guard_mode() ? GUARD_BYTES : 0;
+    // checked mode: no headroom, so that the band starts right behind the bytes the caller asked for (rounded to 256)
+    size_t want = G ? bytes : bytes + bytes / 8;  // headroom so slowly growing inputs do not thrash
     want = (want + 255) & ~(size_t)255;
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, want);
+    cudaError_t e = cudaMalloc(&p, want + 2 * G);
     if (e != cudaSuccess) {
         cudaGetLastError();
         want = (bytes + 255) & ~(size_t)255;
-        e = cudaMalloc(&p, want);
+        e = cudaMalloc(&p, want + 2 * G);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -89,9 +104,32 @@ void* hmse_scratch(hmse_ctx* ctx, int slot, size_t bytes) {
                  cudaGetErrorString(e));
         return nullptr;
     }
-    ctx->slot[slot] = p;
+    if (G) {
+        cudaMemset(p, 0xA5, G);
+        cudaMemset((uint8_t*)p + G + want, 0xA5, G);
+    }
+    ctx->slot_base[slot] = p;
+    ctx->slot[slot] = (uint8_t*)p + G;
     ctx->slot_bytes[slot] = want;
-    return p;
+    return ctx->slot[slot];
+}
+
+HMSE_API int hmse_guard_check(hmse_ctx* ctx) {
+    if (!ctx) return HMSE_E_INVAL;
+    if (!guard_mode()) HMSE_FAIL(ctx, HMSE_E_INVAL, "hmse_guard_check: the library runs without guard bands (set HMSE_GUARD=1 before loading it)");
+    HMSE_CUDA(ctx, cudaDeviceSynchronize());
+    static thread_local uint8_t host[2 * GUARD_BYTES];
+    for (int s = 0; s < SLOT_COUNT; s++) {
+        if (!ctx->slot[s]) continue;
+        uint8_t* base = (uint8_t*)ctx->slot_base[s];
+        HMSE_CUDA(ctx, cudaMemcpy(host, base, GUARD_BYTES, cudaMemcpyDeviceToHost));
+        HMSE_CUDA(ctx, cudaMemcpy(host + GUARD_BYTES, base + GUARD_BYTES + ctx->slot_bytes[s], GUARD_BYTES, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < 2 * GUARD_BYTES; i++)
+            if (host[i] != 0xA5)
+                HMSE_FAIL(ctx, HMSE_E_INVAL, "scratch slot %d (%zu bytes): guard band overwritten %s the slot, byte %zu of the band", s,
+                          ctx->slot_bytes[s], i < GUARD_BYTES ? "BEFORE" : "BEHIND", i % GUARD_BYTES);
+    }
+    return HMSE_OK;
 }
 
 namespace {

@@ -58,6 +58,7 @@ struct hmse_ctx {
     char err[512];
     void* slot[SLOT_COUNT];
     size_t slot_bytes[SLOT_COUNT];
+    void* slot_base[SLOT_COUNT];  // what cudaMalloc returned (= slot[] unless guard bands surround the slot, HMSE_GUARD)
     uint64_t* pinned;  // small pinned host mailbox (HMSE_MAILBOX_BYTES), mapped: kernels write results into it directly
     uint64_t* pinned_dev;  // its device-side address
     int sm_count;

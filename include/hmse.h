@@ -60,6 +60,11 @@ const char* hmse_last_error(hmse_ctx* ctx);
 /* Bytes of device scratch currently held by ctx. */
 uint64_t hmse_scratch_bytes(hmse_ctx* ctx);
 
+/* Checked mode (test suite): with HMSE_GUARD=1 in the environment when the library is loaded, every scratch slot of a ctx
+ * is surrounded by two 4 KiB guard bands; hmse_guard_check synchronises the device and fails with HMSE_E_INVAL (text
+ * names the slot) when a kernel wrote outside its slot.  Without HMSE_GUARD it returns HMSE_E_INVAL. */
+int hmse_guard_check(hmse_ctx* ctx);
+
 /* ---- Measurement hooks (bench.py).  With timing enabled every entry point brackets its kernels
  *      with CUDA events on `stream`; hmse_timing_ms returns the last recorded span of a region. -- */
 #define HMSE_T_SCAN 0

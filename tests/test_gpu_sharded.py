@@ -75,8 +75,9 @@ if kept.numel():
     is_ext = bl_ >= n_
     both = torch.cat([d, gl["ext_data"]])
     e_ = (bl_ - n_).clamp(min=0)
-    boff = torch.where(is_ext, d.numel() + gl["ext_off"][e_], starts_[bl_.clamp(max=n_ - 1)])
-    blen = torch.where(is_ext, gl["ext_off"][e_ + 1] - gl["ext_off"][e_], lens_[bl_.clamp(max=n_ - 1)]).to(torch.int32)
+    eo_ = torch.cat([gl["ext_off"], gl["ext_off"][-1:]])       # (torch.where evaluates both sides: keep e_ + 1 in range)
+    boff = torch.where(is_ext, d.numel() + eo_[e_], starts_[bl_.clamp(max=n_ - 1)])
+    blen = torch.where(is_ext, eo_[e_ + 1] - eo_[e_], lens_[bl_.clamp(max=n_ - 1)]).to(torch.int32)
     out_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=d.device), torch.cumsum(lens_[kept], 0)])
     doff = torch.cat([g4.delta_offsets[kept], g4.delta_offsets[-1:]])
     rebuilt, st_, bad_ = ctx.delta_apply(g4.delta_blob, doff, both, boff.contiguous(), blen.contiguous(), out_off)
