@@ -15,6 +15,8 @@
 //                  the chain merges with the speculative one (chains converge in a few
 //                  chunks); rounds repeat until no segment exit changes.  The same mechanism
 //                  stitches byte-range shards across GPUs (hmse_chunk_resolve with `entry`).
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 namespace {
@@ -30,12 +32,20 @@ struct CdcDev {
 // ------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 256;
 constexpr int K1_RUN = 128;                     // bytes rolled per thread per tile (+64 of warm-up)
-constexpr int K1_CTAS = 3;                      // resident CTAs per SM: the staging buffers, not the registers, bound it
 constexpr int K1_TILE = K1_THREADS * K1_RUN;    // 32 KiB
 constexpr int K1_SLOT = K1_RUN + 16;            // padded slot stride: LDS.128 conflict-free
 constexpr int K1_STAGE = (K1_THREADS + 1) * K1_SLOT;  // slot 0 carries the 64-byte halo
-constexpr int K1_STAGES = 2;
-constexpr size_t K1_SMEM = (size_t)K1_STAGES * K1_STAGE + 256 * 8 + 64;
+// The Gear table lookup is one 8-byte shared-memory load per byte at a data-dependent index: with ONE copy of the 2 KB
+// table the sixteen lanes of a half-warp (a 64-bit load is served per half-warp) fall on sixteen bank pairs at random -
+// about three wavefronts per half-warp instead of one, which is what bounded the kernel (1.2 TB/s, 0.19 of HBM).  With
+// REP = 16 copies, one per bank pair (row e = the sixteen copies of entry e, lane l reads copy l & 15), every lookup is
+// conflict free.  The copies cost 32 KB per CTA, so the staging gives up its second buffer: three CTAs per SM overlap one
+// another's TMA waits instead of each CTA overlapping its own.
+template <int STAGES, int REP>
+struct K1Cfg {
+    static constexpr int CTAS = (STAGES == 1 || REP == 1) ? 3 : 2;   // resident CTAs per SM (shared memory bounds it)
+    static constexpr size_t SMEM = (size_t)STAGES * K1_STAGE + (size_t)REP * 256 * 8 + 64;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,7 +79,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 #define GEAR_STEP(BYTE, BITPOS)                                      \
     {                                                                \
-        fp = (fp << 1) + sg[(BYTE)];                                 \
+        fp = (fp << 1) + sg[(BYTE) * REP];                           \
         if ((fp & mc) == 0) {                                        \
             if ((fp & ms) == 0) sb |= 1ull << (BITPOS);              \
             if ((fp & ml) == 0) lb |= 1ull << (BITPOS);              \
@@ -82,25 +92,32 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     GEAR_STEP(((W) >> 16) & 0xffu, (B0) + 2)   \
     GEAR_STEP((W) >> 24, (B0) + 3)
 
-#define WARM_WORD(W)                              \
-    fp = (fp << 1) + sg[(W) & 0xffu];             \
-    fp = (fp << 1) + sg[((W) >> 8) & 0xffu];      \
-    fp = (fp << 1) + sg[((W) >> 16) & 0xffu];     \
-    fp = (fp << 1) + sg[(W) >> 24];
+#define WARM_WORD(W)                                    \
+    fp = (fp << 1) + sg[((W) & 0xffu) * REP];           \
+    fp = (fp << 1) + sg[(((W) >> 8) & 0xffu) * REP];    \
+    fp = (fp << 1) + sg[(((W) >> 16) & 0xffu) * REP];   \
+    fp = (fp << 1) + sg[((W) >> 24) * REP];
 
-__global__ void __launch_bounds__(K1_THREADS, K1_CTAS)
+template <int STAGES, int REP>
+__global__ void __launch_bounds__(K1_THREADS, (K1Cfg<STAGES, REP>::CTAS))
 gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles, const CdcDev* __restrict__ cfg,
                  uint64_t* __restrict__ bitS, uint64_t* __restrict__ bitL) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage0 = smem;
-    uint64_t* sg = reinterpret_cast<uint64_t*>(smem + (size_t)K1_STAGES * K1_STAGE);
-    uint64_t* bars = sg + 256;  // K1_STAGES barriers
+    uint64_t* sg_all = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * K1_STAGE);
+    uint64_t* bars = sg_all + REP * 256;  // STAGES barriers
     const unsigned t = threadIdx.x;
 
-    sg[t] = cfg->gear[t];
+    {
+        const uint64_t g = cfg->gear[t];
+#pragma unroll
+        for (int c = 0; c < REP; c++) sg_all[t * REP + c] = g;
+    }
+    // sg[b * REP] = this lane's copy of entry b (its own bank pair when REP == 16)
+    const uint64_t* sg = sg_all + (REP > 1 ? (t & (REP - 1)) : 0);
     const uint64_t ms = cfg->ms, ml = cfg->ml, mc = cfg->mc;
     if (t == 0) {
-        for (int s = 0; s < K1_STAGES; s++) mbar_init(&bars[s], K1_THREADS);
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], K1_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -123,12 +140,18 @@ gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles,
     };
 
     uint64_t tile = blockIdx.x;
-    if (tile < n_tiles) issue(tile, 0);
+    if (STAGES == 2 && tile < n_tiles) issue(tile, 0);
     for (uint32_t it = 0; tile < n_tiles; it++, tile += gridDim.x) {
-        const int s = it & 1;
-        const uint64_t next = tile + gridDim.x;
-        if (next < n_tiles) issue(next, s ^ 1);
-        mbar_wait(&bars[s], (it >> 1) & 1);
+        int s = 0;
+        if (STAGES == 2) {
+            s = it & 1;
+            const uint64_t next = tile + gridDim.x;
+            if (next < n_tiles) issue(next, s ^ 1);
+            mbar_wait(&bars[s], (it >> 1) & 1);
+        } else {
+            issue(tile, 0);                 // one buffer: the other CTAs of the SM compute while this copy is in flight
+            mbar_wait(&bars[0], it & 1);
+        }
 
         const uint8_t* st = stage0 + (size_t)s * K1_STAGE;
         const uint64_t pos = tile * (uint64_t)K1_TILE + (uint64_t)t * K1_RUN;
@@ -436,14 +459,30 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
     const uint64_t words = (n_tiles ? n_tiles : 1) * (K1_TILE / 64);
     HMSE_SCRATCH(ctx, bits, uint64_t*, SLOT_CDC_BITS, 2 * words * sizeof(uint64_t));
     if (n_tiles) {
-        HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)K1_SMEM));
-        const uint64_t resident = (uint64_t)ctx->sm_count * K1_CTAS;
-        uint64_t grid = n_tiles < resident ? n_tiles : resident;
+        // variant: 1 = replicated table, one staging buffer, 3 CTAs per SM (default); 2 = replicated table, two buffers, 2 CTAs;
+        // 0 = single table, two buffers, 3 CTAs (the round-1 kernel).  HMSE_SCAN_VARIANT selects one for measurements.
+        static int variant = -1;
+        if (variant < 0) {
+            const char* e = getenv("HMSE_SCAN_VARIANT");
+            variant = e ? atoi(e) : 1;
+            if (variant < 0 || variant > 2) variant = 1;
+        }
+        const CdcDev* dc = (const CdcDev*)ctx->slot[SLOT_CDC_CFG];
         HT_BEGIN(ctx, HT_SCAN, st);
         KL(ctx);
-        gear_scan_kernel<<<(unsigned)grid, K1_THREADS, K1_SMEM, st>>>(
-            d_data, n_avail, n_tiles, (const CdcDev*)ctx->slot[SLOT_CDC_CFG], bits, bits + words);
+#define K1_LAUNCH(ST, RP)                                                                                                     \
+    {                                                                                                                         \
+        HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_kernel<ST, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                            (int)K1Cfg<ST, RP>::SMEM));                                                       \
+        const uint64_t resident = (uint64_t)ctx->sm_count * K1Cfg<ST, RP>::CTAS;                                              \
+        const uint64_t grid = n_tiles < resident ? n_tiles : resident;                                                        \
+        gear_scan_kernel<ST, RP><<<(unsigned)grid, K1_THREADS, K1Cfg<ST, RP>::SMEM, st>>>(d_data, n_avail, n_tiles, dc, bits, \
+                                                                                          bits + words);                      \
+    }
+        if (variant == 0) K1_LAUNCH(2, 1)
+        else if (variant == 2) K1_LAUNCH(2, 16)
+        else K1_LAUNCH(1, 16)
+#undef K1_LAUNCH
         HMSE_LAUNCH_CHECK(ctx);
         HT_END(ctx, HT_SCAN, st);
     }

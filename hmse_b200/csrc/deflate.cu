@@ -8,9 +8,9 @@
 //
 //  parse_kernel    one CTA per chunk (persistent, two size classes).
 //     P0 stage chunk in shared memory + Adler-32      P4 match search, one thread per SORTED index
-//     P1 4-byte hashes (13 bits) of every position       (lanes of a warp share a bucket: similar
-//     P2 / P3 stable two-pass radix sort of the            chain lengths, broadcast loads), own
-//        positions by hash (warp-local MATCH ranks)       buckets in shared memory, dictionary
+//     P1 histogram of 4-byte hashes (13 bits)            (lanes of a warp share a bucket: similar
+//     P2 scan -> bucket starts                            chain lengths, broadcast loads), own
+//     P3 tile-ordered scatter + bucket fix-up sort        buckets in shared memory, dictionary
 //        (positions ascending: nearest-first search,      buckets (host-built index) from L1/L2
 //        deterministic output)                         P5 per-32-byte-range backward DP of chain exits
 //                                                      P6 hop the true chain across ranges
@@ -49,6 +49,7 @@ constexpr uint32_t DICT_MAX = 32768;
 // 87 % of the bytes are small (<= 13 KiB: the most that lets two CTAs share an SM), 12.5 % medium (13-20 KiB), < 0.5 % large.
 constexpr uint32_t NMAX_SMALL = 13312, NMAX_MEDIUM = 20480, NMAX_LARGE = 32768;
 constexpr int N_CLASS = 3, LONG_CLASS = 3;   // class 3: longer than NMAX_LARGE (multi-block streams)
+static_assert(NMAX_LARGE / 512 <= 64, "P3b keeps one moved-bit per element of a thread");
 constexpr int T_PARSE = 512;
 constexpr int TILE_SHIFT = 9;       // log2(T_PARSE): a scatter tile is T_PARSE consecutive positions
 static_assert((1 << TILE_SHIFT) == T_PARSE, "TILE_SHIFT");
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     const uint8_t* s_data = smem;
     uint16_t* s_sorted = reinterpret_cast<uint16_t*>(smem + nmax + 16);        // nmax u16 (later: exits, skewed)
     uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + nmax + 16 + 2 * (size_t)(nmax + nmax / 32));  // CNT_WORDS
+    uint16_t* s_E = reinterpret_cast<uint16_t*>(s_cnt32);  // bucket h = sorted[E[h] .. E[h+1])
     uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CNT_WORDS);         // nmax/16 bytes: entry offset of every range
     ParseSm* sm = reinterpret_cast<ParseSm*>(s_entry + nmax / 16);
     uint8_t* s_tail = reinterpret_cast<uint8_t*>(sm) + ((sizeof(ParseSm) + 15) & ~15u);
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 }
                 s_data32[i] = v;
             }
+            for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;
             for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
             sb %= 65521u;
             // only the two block totals are needed: one REDUX per warp, sixteen partial sums in shared memory
@@ -342,87 +345,147 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
         // which are not written before P4)
         uint16_t* s_h16 = reinterpret_cast<uint16_t*>(mptr) + nmax;
         if (a.level != 0) {
-            // ---- P1: the 13-bit hash of every position, four positions per step from two words ----
+            // ---- P1: hash histogram (count of bucket h lives at E[h+1]); four positions per step from two words ----
             for (uint32_t i = t; 4 * i < nh; i += T) {
                 const uint32_t w0 = s_data32[i], w1 = s_data32[i + 1];
                 uint32_t hh[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) hh[q] = hash4(q ? __funnelshift_r(w0, w1, 8 * q) : w0);
+                for (int q = 0; q < 4; q++) {
+                    hh[q] = hash4(q ? __funnelshift_r(w0, w1, 8 * q) : w0);
+                    if (4 * i + q < nh) {
+                        const uint32_t h1 = hh[q] + 1;
+                        atomicAdd(&s_cnt32[h1 >> 1], 1u << (16 * (h1 & 1)));
+                    }
+                }
                 reinterpret_cast<uint2*>(s_h16)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
             }
             __syncthreads();
-            PROF(2)
-            // ---- P2 / P3: positions sorted by (hash, position): a STABLE least-significant-digit radix sort, the low 7
-            //      bits of the hash, then the high 6.  A warp owns a contiguous span of the pass's input and walks it 32
-            //      elements at a time: the lanes of a step that share a digit are found with one MATCH (ranks inside the
-            //      step = lane order), counters are per (warp, digit), and the scan runs digit-major / warp-minor, so
-            //      equal digits keep their input order - buckets come out ascending by position (nearest-first candidates,
-            //      deterministic output) with no atomics and no repair pass (the earlier bucket scatter ordered a bucket only
-            //      up to a 512-position tile and needed a fix-up sort that cost 12 % of the kernel's instructions).
+            // ---- P2: exclusive scan: E[h+1] = start of bucket h (cursor), E[0] = 0.  E[0] holds no count, so this is
+            //      the exclusive scan of the u16 array E[0 .. NBUCKET] itself.  A warp owns 256 consecutive words (512
+            //      entries) and reads them row by row, lane = word: conflict-free, where a thread walking its own 16
+            //      consecutive entries put eight lanes on every bank (a fifth of the kernel's shared-memory wavefronts).
             {
-                uint16_t* s_tmp16 = reinterpret_cast<uint16_t*>(mptr);   // pass-1 output (match words are not written before P4)
-                uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_cnt32);  // [warp][digit] counters, then cursors
-                const uint32_t lt = (1u << lane) - 1;
-                const uint32_t per = ((nh + T - 1) / T) * 32;             // elements per warp, a multiple of 32
-                const uint32_t lo = warp * per, hi = lo + per < nh ? lo + per : nh;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; pass++) {
-                    const uint32_t ND = pass ? 64u : 128u, shift = pass ? 7u : 0u;
-                    const uint16_t* src = pass ? s_tmp16 : nullptr;       // pass 0 reads the identity order
-                    uint16_t* dst = pass ? s_sorted : s_tmp16;
-                    for (uint32_t i = t; i < ND * (T_PARSE / 32) / 2; i += T) s_cnt32[i] = 0;
-                    __syncthreads();
-                    uint16_t* my = s_wcnt + warp * ND;
-                    for (uint32_t b0 = lo; b0 < hi; b0 += 32) {           // warp-uniform trip count
-                        const uint32_t i = b0 + lane;
-                        const bool valid = i < hi;
-                        const uint32_t pos = valid ? (src ? (uint32_t)src[i] : i) : 0u;
-                        const uint32_t dg = valid ? ((uint32_t)s_h16[pos] >> shift) & (ND - 1) : 0x100u + lane;
-                        const uint32_t peers = __match_any_sync(0xffffffffu, dg);
-                        if (valid && (peers & lt) == 0) my[dg] = (uint16_t)(my[dg] + __popc(peers));
-                        __syncwarp();
-                    }
-                    __syncthreads();
-                    // exclusive scan in (digit, warp) order: thread d owns digit d's sixteen counters
-                    {
-                        uint32_t c[T_PARSE / 32], tot = 0;
-                        if (t < ND) {
+                static_assert(NBUCKET / 2 == 256 * (T_PARSE / 32), "one 256-word span per warp");
+                uint32_t* wp = s_cnt32 + warp * 256 + lane;
+                uint32_t wv[8], pre[8], carry = 0;
 #pragma unroll
-                            for (int w = 0; w < T_PARSE / 32; w++) {
-                                c[w] = s_wcnt[w * ND + t];
-                                tot += c[w];
-                            }
-                        }
-                        uint32_t dummy;
-                        uint32_t run = block_excl_scan(tot, sm->warp_tmp, &dummy);
-                        if (t < ND) {
+                for (int r = 0; r < 8; r++) {
+                    wv[r] = wp[r * 32];
+                    const uint32_t sum2 = (wv[r] & 0xffffu) + (wv[r] >> 16);
+                    uint32_t inc = sum2;
 #pragma unroll
-                            for (int w = 0; w < T_PARSE / 32; w++) {
-                                s_wcnt[w * ND + t] = (uint16_t)run;
-                                run += c[w];
-                            }
-                        }
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (unsigned)o) inc += tt;
                     }
-                    __syncthreads();
-                    for (uint32_t b0 = lo; b0 < hi; b0 += 32) {
-                        const uint32_t i = b0 + lane;
-                        const bool valid = i < hi;
-                        const uint32_t pos = valid ? (src ? (uint32_t)src[i] : i) : 0u;
-                        const uint32_t dg = valid ? ((uint32_t)s_h16[pos] >> shift) & (ND - 1) : 0x100u + lane;
-                        const uint32_t peers = __match_any_sync(0xffffffffu, dg);
-                        const uint32_t rank = __popc(peers & lt);
-                        const uint32_t base = valid ? (uint32_t)my[dg] : 0u;
-                        __syncwarp();
-                        if (valid) {
-                            dst[base + rank] = (uint16_t)pos;
-                            if (rank == 0) my[dg] = (uint16_t)(base + __popc(peers));
-                        }
-                        __syncwarp();
+                    pre[r] = carry + inc - sum2;
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0) sm->warp_tmp[warp] = carry;
+                __syncthreads();
+                if (warp == 0) {
+                    const uint32_t v = lane < nwarps ? sm->warp_tmp[lane] : 0u;
+                    uint32_t inc = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (unsigned)o) inc += tt;
                     }
-                    __syncthreads();
+                    sm->warp_tmp[lane] = inc - v;
+                    if (lane == 31) s_E[NBUCKET] = (uint16_t)inc;   // the entry past the last full word: everything before it
+                }
+                __syncthreads();
+                const uint32_t base = sm->warp_tmp[warp];
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const uint32_t e0 = base + pre[r];
+                    wp[r * 32] = e0 | ((e0 + (wv[r] & 0xffffu)) << 16);
                 }
             }
+            __syncthreads();
+            PROF(2)
+            // ---- P3: scatter tile by tile (cursors count up to the bucket ends): buckets end up
+            //      ordered by position except inside a tile, then every bucket is put in order ----
+            for (uint32_t p0 = 0; p0 < nh; p0 += T) {
+                const uint32_t p = p0 + t;
+                if (p < nh) {
+                    const uint32_t h1 = (uint32_t)s_h16[p] + 1;
+                    const uint32_t sh = 16 * (h1 & 1);
+                    const uint32_t old = atomicAdd(&s_cnt32[h1 >> 1], 1u << sh);
+                    s_sorted[(old >> sh) & 0xffffu] = (uint16_t)p;
+                }
+                __syncthreads();
+            }
             PROF(3)
+            // Buckets are already ordered except for same-hash positions that were scattered in the same
+            // tile (common in text: a word repeated within 512 bytes).  Such a group is contiguous in the
+            // bucket.  Pass 1 (all elements, cheap): an element whose neighbours both come from other tiles is in
+            // place; the others are compacted into a list.  Pass 2 (dense over the list): a listed element finds
+            // its rank inside its group (a neighbour belongs to the same bucket iff its stored hash agrees; groups
+            // are tiny) and writes itself to a temporary copy.  Pass 3 copies the moved elements back.
+            uint16_t* s_tmp16 = reinterpret_cast<uint16_t*>(mptr);   // match words are not written before P4
+            uint16_t* s_list = s_E;                                    // the cursors are dead; bit 15 = "moved"
+            constexpr uint32_t LIST_CAP = CNT_WORDS * 2;
+            uint64_t moved = 0;   // elements handled in line because the list was full: bit k = index t' + k*T moved
+            auto fix_member = [&](uint32_t i) -> bool {
+                const uint32_t p = s_sorted[i];
+                const uint32_t tile = p >> TILE_SHIFT;
+                const uint32_t h = s_h16[p];
+                uint32_t first = i, smaller = 0, others = 0;
+                for (uint32_t j = i; j > 0;) {   // left neighbours of the same tile and bucket
+                    j--;
+                    const uint32_t q = s_sorted[j];
+                    if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
+                    first = j;
+                    smaller += q < p;
+                    others++;
+                }
+                for (uint32_t j = i + 1; j < nh; j++) {
+                    const uint32_t q = s_sorted[j];
+                    if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
+                    smaller += q < p;
+                    others++;
+                }
+                if (others) s_tmp16[first + smaller] = (uint16_t)p;
+                return others != 0;
+            };
+            // every warp keeps its own list (a shared list head would serialise the sixteen warps on one atomic)
+            constexpr uint32_t WCAP = LIST_CAP / (T_PARSE / 32);
+            uint16_t* wlist = s_list + warp * WCAP;
+            uint32_t wcnt = 0;   // warp-uniform
+            {
+                uint32_t k = 0;
+                for (uint32_t ib = warp * 32; ib < nh; ib += T, k++) {   // warp-uniform trip count
+                    const uint32_t i = ib + lane;
+                    bool cand = false;
+                    if (i < nh) {
+                        const uint32_t tile = (uint32_t)s_sorted[i] >> TILE_SHIFT;
+                        const uint32_t ql = i ? s_sorted[i - 1] : 0xffffffffu, qr = i + 1 < nh ? s_sorted[i + 1] : 0xffffffffu;
+                        cand = (ql >> TILE_SHIFT) == tile || (qr >> TILE_SHIFT) == tile;
+                    }
+                    const uint32_t b = __ballot_sync(0xffffffffu, cand);
+                    if (cand) {
+                        const uint32_t slot = wcnt + __popc(b & ((1u << lane) - 1));
+                        if (slot < WCAP) wlist[slot] = (uint16_t)i;
+                        else if (fix_member(i)) moved |= 1ull << k;   // (only on highly repetitive chunks)
+                    }
+                    wcnt += __popc(b);
+                }
+            }
+            __syncwarp();
+            const uint32_t n_list = wcnt < WCAP ? wcnt : WCAP;
+            for (uint32_t j = lane; j < n_list; j += 32)
+                if (fix_member(wlist[j])) wlist[j] |= 0x8000u;
+            __syncthreads();   // every group has been read before any element moves
+            for (uint32_t j = lane; j < n_list; j += 32) {
+                const uint32_t e = wlist[j];
+                if (e & 0x8000u) s_sorted[e & 0x7fffu] = s_tmp16[e & 0x7fffu];
+            }
+            for (uint64_t mm = moved; mm; mm &= mm - 1) {
+                const uint32_t i = warp * 32 + lane + (uint32_t)(__ffsll((long long)mm) - 1) * T;
+                s_sorted[i] = s_tmp16[i];
+            }
+            __syncthreads();
             PROF(4)
             // ---- P4: matches as RUNS.  A pair (position p, source q) whose four bytes agree and whose
             //      preceding bytes differ starts a run: every position p+k inside it has a match of
@@ -599,7 +662,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             //      hops block to block through those tables; (c) lane 0 of every warp re-walks its block
             //      from the true entry and marks the per-range entries. -----------------------------------
             {
-                uint16_t* s_bexit = reinterpret_cast<uint16_t*>(s_cnt32);   // [block][64]: exit of a chain entering the block at offset o
+                uint16_t* s_bexit = s_E;          // [block][258]: exit of a chain entering the block at offset o (E is dead)
                 uint16_t* s_bentry = sm->bentry;  // [block]: true entry position (0xFFFF = not visited)
                 const uint32_t NB = (n + 1023) >> 10;
                 // (a) a chain almost always enters a block within its first 64 positions (only a match
