@@ -649,10 +649,16 @@ def run_ours(args):
                    "offsets, compressed blob) overlap on three CUDA streams; the next step's input is copied in behind the "
                    "current step's (two device input buffers)" % args.piece_mib)
 
+            step_trace = []
+
             def e2e_steps(k):
-                nonlocal d2h
+                nonlocal d2h, step_trace
+                stream_pipe.trace = []
                 for r in stream_pipe.run_many([host_in] * k, host_blob_cap=n_avail // 2 + (1 << 20)):
                     d2h = r.d2h_bytes
+                    step_trace = [(lab, round(ms_, 1)) for lab, ms_ in stream_pipe.trace]   # host ms since this step's run() began
+                    stream_pipe.trace = []
+                stream_pipe.trace = None
         else:
             host_out = pipe.host_buffers(n_avail)
             api = ("hmse_b200.ShardedIngest.run_batches(pinned host shard buffers, host=pinned result buffers): every step's "
@@ -675,7 +681,7 @@ def run_ours(args):
         e2e_steps(k_e2e)
         a1.record()
         barrier()
-        timeline = None
+        timeline = step_trace if world == 1 else None
         if world > 1 and pipe.trace:
             # rank 0, per batch, ms since the timed region began: copy-in start / end, pipeline start, all results on the host
             timeline = [[round(a0.elapsed_time(ev), 1) for ev in tup] for tup in pipe.trace]

@@ -35,12 +35,8 @@ constexpr int K1_RUN = 128;                     // bytes rolled per thread per t
 constexpr int K1_TILE = K1_THREADS * K1_RUN;    // 32 KiB
 constexpr int K1_SLOT = K1_RUN + 16;            // padded slot stride: LDS.128 conflict-free
 constexpr int K1_STAGE = (K1_THREADS + 1) * K1_SLOT;  // slot 0 carries the 64-byte halo
-// The Gear table lookup is one 8-byte shared-memory load per byte at a data-dependent index: with ONE copy of the 2 KB
-// table the sixteen lanes of a half-warp (a 64-bit load is served per half-warp) fall on sixteen bank pairs at random -
-// about three wavefronts per half-warp instead of one, which is what bounded the kernel (1.2 TB/s, 0.19 of HBM).  With
-// REP = 16 copies, one per bank pair (row e = the sixteen copies of entry e, lane l reads copy l & 15), every lookup is
-// conflict free.  The copies cost 32 KB per CTA, so the staging gives up its second buffer: three CTAs per SM overlap one
-// another's TMA waits instead of each CTA overlapping its own.
+// REP > 1 keeps REP copies of the Gear table, one per bank pair (row e = the copies of entry e, lane l reads copy l & 15), so
+// that the data-dependent 8-byte lookups of a half-warp never share a bank.  Measured (see hmse_chunk_scan): no gain.
 template <int STAGES, int REP>
 struct K1Cfg {
     static constexpr int CTAS = (STAGES == 1 || REP == 1) ? 3 : 2;   // resident CTAs per SM (shared memory bounds it)
@@ -459,13 +455,16 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
     const uint64_t words = (n_tiles ? n_tiles : 1) * (K1_TILE / 64);
     HMSE_SCRATCH(ctx, bits, uint64_t*, SLOT_CDC_BITS, 2 * words * sizeof(uint64_t));
     if (n_tiles) {
-        // variant: 1 = replicated table, one staging buffer, 3 CTAs per SM (default); 2 = replicated table, two buffers, 2 CTAs;
-        // 0 = single table, two buffers, 3 CTAs (the round-1 kernel).  HMSE_SCAN_VARIANT selects one for measurements.
+        // variant 0 (default): one copy of the Gear table, two staging buffers, 3 CTAs per SM.  HMSE_SCAN_VARIANT selects the
+        // two measured alternatives (tools/scan_variants.py, profiles/r02f_scan_variants.txt): 1 = table replicated 16 times
+        // (one copy per bank pair, lookups conflict free), one staging buffer, 3 CTAs; 2 = replicated, two buffers, 2 CTAs.
+        // Measured on B200 over 10 GB: 8.14 / 8.70 / 9.03 ms - the replicated table is NOT faster, so bank conflicts of the
+        // lookup do not bound this kernel (the serial fp chain and the issue rate do); the variants stay for the record.
         static int variant = -1;
         if (variant < 0) {
             const char* e = getenv("HMSE_SCAN_VARIANT");
-            variant = e ? atoi(e) : 1;
-            if (variant < 0 || variant > 2) variant = 1;
+            variant = e ? atoi(e) : 0;
+            if (variant < 0 || variant > 2) variant = 0;
         }
         const CdcDev* dc = (const CdcDev*)ctx->slot[SLOT_CDC_CFG];
         HT_BEGIN(ctx, HT_SCAN, st);
