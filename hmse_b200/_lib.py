@@ -25,7 +25,8 @@ class CdcCfg(C.Structure):
 
 
 class CorpusCfg(C.Structure):
-    _fields_ = [("seed", C.c_uint32), ("dup_thr", C.c_uint32), ("near_thr", C.c_uint32), ("n_lex", C.c_uint32)]
+    _fields_ = [("seed", C.c_uint32), ("dup_thr", C.c_uint32), ("near_thr", C.c_uint32), ("n_lex", C.c_uint32),
+                ("pick_tries", C.c_uint32)]
 
 
 _P, _U64, _U32, _I = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int

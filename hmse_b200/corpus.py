@@ -84,10 +84,12 @@ class CorpusConfig:
     seed: int = 42
     dup_thr: int = 184
     near_thr: int = 358
+    pick_tries: int = 4     # attempts to find an earlier article of the unique class to copy from
 
     @staticmethod
     def high_redundancy(seed: int = 42) -> "CorpusConfig":
-        return CorpusConfig(seed, 655, 164)
+        """83 % of the articles are copies of articles that occurred earlier: >= 60 % of the chunks are exact duplicates."""
+        return CorpusConfig(seed, 850, 70, 32)
 
 
 class DeviceCorpus:
@@ -100,7 +102,7 @@ class DeviceCorpus:
         blob, off = lexicon()
         self.lex_blob = torch.from_numpy(blob).to(ctx.tdev)
         self.lex_off = torch.from_numpy(off.view(np.int32).copy()).to(ctx.tdev)
-        self.c = CorpusCfg(cfg.seed, cfg.dup_thr, cfg.near_thr, off.size - 1)
+        self.c = CorpusCfg(cfg.seed, cfg.dup_thr, cfg.near_thr, off.size - 1, cfg.pick_tries)
         self._offs = None  # int64 stream offsets of articles 0.._n_art (device), grown on demand
 
     def _ensure(self, end_byte: int):

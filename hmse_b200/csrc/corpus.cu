@@ -46,7 +46,8 @@ __device__ __forceinline__ Meta article_meta(const hmse_corpus_cfg& cfg, uint64_
         const uint32_t cls = H(cfg.seed, a, K_CLASS) & 1023;
         if (cls < thr) {
             uint32_t c = 0;
-            for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t tries = cfg.pick_tries ? cfg.pick_tries : 4u;
+            for (uint32_t k = 0; k < tries; k++) {
                 c = (uint32_t)(((uint64_t)H(cfg.seed, a, K_PICK + k) * a) >> 32);
                 if (c == 0 || (H(cfg.seed, c, K_CLASS) & 1023) >= thr) break;
             }

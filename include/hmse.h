@@ -350,6 +350,7 @@ typedef struct hmse_corpus_cfg {
     uint32_t dup_thr;
     uint32_t near_thr;
     uint32_t n_lex; /* lexicon entries */
+    uint32_t pick_tries; /* attempts of a copy article to find an earlier article of the unique class (0 = 4) */
 } hmse_corpus_cfg;
 /* d_art_len[n_articles] (u32) = byte length of each article first_article.. */
 int hmse_corpus_lengths(hmse_ctx* ctx, const hmse_corpus_cfg* cfg, const uint32_t* d_lex_off,
