@@ -68,9 +68,12 @@ constexpr uint32_t REC_WORDS = 320;                          // 288 lit/len + 32
 
 // Device image of the dictionary index (SLOT_DEFLATE_DICT), built on the host once per dictionary.
 // One 16-byte record per bucket of 4-byte hashes: the four nearest (largest position first) dictionary
-// positions of that bucket, each as  valid << 31 | tag << 23 | prev << 15 | pos  where tag = eight more
-// bits of the hash (a filter: phase B compares the real bytes) and prev = the byte before pos
-// (DICT_PREV0 before position 0).  One LDG.128 per chunk position screens all four candidates.
+// positions of that bucket, each in the "K" layout that parse_kernel also gives every chunk position:
+//     pos << 17 | 1 << 16 (valid) | tag << 8 | prev
+// tag = byte 1 of the hash product (a filter only: phase B compares the real bytes), prev = the byte before pos
+// (DICT_PREV0 before position 0).  One LDG.128 per chunk position screens all four candidates; a candidate c
+// starts a run at a position with signature s iff ((c ^ s) & 0x1ffff) - 1 < 0xff (both valid, same tag, different
+// previous byte), and it lies inside the window iff c >= threshold << 17 - two compares per candidate.
 constexpr uint32_t DICT_PREV0 = 0xFFu, CHUNK_PREV0 = 0xFEu;   // never equal: (0, 0) is always a run head
 struct DictDev {
     uint8_t bytes[DICT_MAX + 32];
@@ -104,7 +107,6 @@ struct DeflArgs {
     const uint8_t* stored_flag; // stored_kernel: only the list entries flagged here (null = all)
     uint32_t job0, job1;     // batch = list[job0 .. job1)
     uint32_t nmax;
-    int match_smem;          // match words live in shared memory (small class) or in `match`
     uint8_t* stage;
     const uint64_t* slot_off;
     uint64_t* sizes;
@@ -128,8 +130,16 @@ __device__ unsigned long long g_prof[16];
     }
 
 constexpr uint32_t CNT_WORDS = NBUCKET / 2 + 36;  // bucket table; later the pair lists, then the 32 x 64 block-exit table
-constexpr uint32_t PAIR_CAP = 256;                // per-warp list of pairs awaiting extension: < 32 left over + 8 x 28 new
-static_assert(PAIR_CAP * (T_PARSE / 32) <= CNT_WORDS, "pair lists must fit in the bucket table");
+// Per-warp lists of (position, source) pairs awaiting extension, one for own-chunk sources and one for dictionary
+// sources (each is extended by code that knows its address space).  A list holds < 32 left-overs plus what one window
+// of 32 - OWN positions can add.
+__host__ __device__ constexpr uint32_t own_cap(int own) { return (31u + (32u - own) * own + 7u) & ~7u; }
+__host__ __device__ constexpr uint32_t dict_cap(int own) { return (31u + (32u - own) * DICT_CAP + 7u) & ~7u; }
+__host__ __device__ constexpr uint32_t cnt_words(int own) {   // words of the bucket-table region (the pair lists may need more than the table)
+    return (own_cap(own) + dict_cap(own)) * (T_PARSE / 32) > CNT_WORDS ? (own_cap(own) + dict_cap(own)) * (T_PARSE / 32) : CNT_WORDS;
+}
+constexpr uint32_t PAD_FRONT = 16;   // bytes before the chunk in shared memory: the last one is the "byte before position 0"
+constexpr uint32_t PAD_SORTED = 16;  // bytes before s_sorted: its last u16 is the sentinel s_sorted[-1]
 
 struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t hist[REC_WORDS];
@@ -141,10 +151,12 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
 
 // Dictionary bucket of a 4-byte value; the own-chunk bucket hash4(v) is its top HASH_BITS bits.
 __host__ __device__ __forceinline__ uint32_t hash_dict(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - DICT_HASH_BITS); }
-// the next eight bits of the same product, placed where the bucket records keep their tag (bits 23..30)
-__host__ __device__ __forceinline__ uint32_t dict_tag23(uint32_t v) {
-    return ((v * 0x9E3779B1u) << (DICT_HASH_BITS - 1)) & 0x7f800000u;
+// K-layout record of position `pos` whose four bytes are v and whose preceding byte is prev
+constexpr uint32_t K_VALID = 0x10000u, K_LOW = 0x1ffffu, K_POS = 0xfffe0000u;
+__host__ __device__ __forceinline__ uint32_t k_record(uint32_t v, uint32_t prev, uint32_t pos) {
+    return (pos << 17) | K_VALID | ((v * 0x9E3779B1u) & 0xff00u) | prev;
 }
+__device__ __forceinline__ bool k_head(uint32_t cand, uint32_t sig) { return ((cand ^ sig) & K_LOW) - 1u < 0xffu; }
 
 __device__ __forceinline__ uint32_t ld32u(const uint32_t* w, uint32_t off) {
     const uint32_t i = off >> 2;
@@ -241,34 +253,57 @@ __device__ __forceinline__ uint32_t extend_run(const uint32_t* d32, const uint32
 // accesses conflict free in shared memory.
 __device__ __forceinline__ uint32_t SK(uint32_t p) { return p + (p >> 5); }
 
+// Shared-memory words addressed by their 32-bit shared-window address: the pair lists of P4 are written by predicated
+// stores (no branch around a one-instruction body, whatever the compiler's mood) and read back the same way.
+__device__ __forceinline__ void sts_if(uint32_t saddr, uint32_t v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.b32 [%0], %1;\n\t}" ::"r"(saddr), "r"(v), "r"((uint32_t)p));
+}
+__device__ __forceinline__ uint32_t lds_w(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // Match word: bits 16..24 length (0 = literal), bit 15 "lazy: emit as literal", bits 0..14 distance-1.
 __device__ __forceinline__ bool mw_is_match(uint32_t mw) { return (mw >> 16) != 0 && !(mw & 0x8000u); }
 
 // =================================================================================================
 // parse_kernel
 // =================================================================================================
-template <int RS, int OWN>   // log2 of the range length of the chain passes P4c-P7; own-chunk candidates per position
+// RS: log2 of the range length of the chain passes P4c-P7; OWN: own-chunk candidates per position; MSM: the match
+// words live in shared memory (small class: every access to them is an LDS/STS/ATOMS with a 32-bit address) or in
+// global scratch (a.match).
+template <int RS, int OWN, bool MSM>
 __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     static_assert(OWN >= 1 && OWN <= OWN_CAP, "own candidates");
     constexpr int WIN = 32 - OWN;   // new sorted indices per window: the first OWN lanes only carry context
     constexpr uint32_t RL = 1u << RS;
+    constexpr uint32_t CW = cnt_words(OWN);
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t T = blockDim.x, t = threadIdx.x;
-    const unsigned lane = t & 31, warp = t >> 5, nwarps = T >> 5;
+    constexpr uint32_t T = T_PARSE;   // the launch uses exactly T_PARSE threads: strides and per-thread shares are constants
+    const uint32_t t = threadIdx.x;
+    const unsigned lane = t & 31, warp = t >> 5;
+    constexpr unsigned nwarps = T >> 5;
     const uint32_t nmax = a.nmax;
-    // layout
-    uint32_t* s_data32 = reinterpret_cast<uint32_t*>(smem);                     // nmax + 16 bytes
-    const uint8_t* s_data = smem;
-    uint16_t* s_sorted = reinterpret_cast<uint16_t*>(smem + nmax + 16);        // nmax u16 (later: exits, skewed)
-    uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + nmax + 16 + 2 * (size_t)(nmax + nmax / 32));  // CNT_WORDS
+    // layout: [PAD_FRONT | chunk, nmax + 16 | PAD_SORTED | sorted | bucket table | range entries | ParseSm | match words]
+    uint32_t* s_data32 = reinterpret_cast<uint32_t*>(smem + PAD_FRONT);            // nmax + 16 bytes
+    const uint8_t* s_data = smem + PAD_FRONT;
+    const size_t o_sorted = (size_t)PAD_FRONT + nmax + 16 + PAD_SORTED;
+    uint16_t* s_sorted = reinterpret_cast<uint16_t*>(smem + o_sorted);            // nmax u16 (later: exits, skewed)
+    uint32_t* s_cnt32 = reinterpret_cast<uint32_t*>(smem + o_sorted + 2 * (size_t)(nmax + nmax / 32));  // CW words
     uint16_t* s_E = reinterpret_cast<uint16_t*>(s_cnt32);  // bucket h = sorted[E[h] .. E[h+1])
-    uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CNT_WORDS);         // nmax/16 bytes: entry offset of every range
+    uint8_t* s_entry = reinterpret_cast<uint8_t*>(s_cnt32 + CW);                  // nmax/16 bytes: entry offset of every range
     ParseSm* sm = reinterpret_cast<ParseSm*>(s_entry + nmax / 16);
     uint8_t* s_tail = reinterpret_cast<uint8_t*>(sm) + ((sizeof(ParseSm) + 15) & ~15u);
     // small class: match words in shared memory (skewed); the list of buckets to sort borrows that
     // space before P4.  large class: match words in global scratch, the list has its own space.
-    uint32_t* mptr = a.match_smem ? reinterpret_cast<uint32_t*>(s_tail) : a.match + (size_t)blockIdx.x * (nmax + nmax / 32);
+    uint32_t* mptr;
+    if constexpr (MSM) mptr = reinterpret_cast<uint32_t*>(s_tail);
+    else mptr = a.match + (size_t)blockIdx.x * (nmax + nmax / 32);
     uint16_t* s_exit = s_sorted;
+    // the byte "before position 0" of every chunk (never equal to DICT_PREV0: (0, 0) is always a run head), so that the
+    // signature of a position needs no special case for p == 0; never overwritten
+    if (t == 0) reinterpret_cast<uint32_t*>(smem)[PAD_FRONT / 4 - 1] = CHUNK_PREV0 << 24;
 
     for (;;) {
         __syncthreads();
@@ -317,7 +352,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 }
                 s_data32[i] = v;
             }
-            for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;
+            for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;   // (the bucket table proper: the rest of the region only holds pair lists)
             for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
             sb %= 65521u;
             // only the two block totals are needed: one REDUX per warp, sixteen partial sums in shared memory
@@ -361,51 +396,66 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             }
             __syncthreads();
             // ---- P2: exclusive scan: E[h+1] = start of bucket h (cursor), E[0] = 0.  E[0] holds no count, so this is
-            //      the exclusive scan of the u16 array E[0 .. NBUCKET] itself.  A warp owns 256 consecutive words (512
-            //      entries) and reads them row by row, lane = word: conflict-free, where a thread walking its own 16
-            //      consecutive entries put eight lanes on every bank (a fifth of the kernel's shared-memory wavefronts).
+            //      the exclusive scan of the u16 array E[0 .. NBUCKET] itself.  A thread owns two 16-byte vectors, one in
+            //      each half of the table (consecutive lanes read consecutive vectors: conflict-free LDS.128), scans its
+            //      16 entries in registers, and ONE block scan carries both halves at once (half A in the low 16 bits of
+            //      the packed sum, half B in the high 16: neither exceeds 32765).
             {
-                static_assert(NBUCKET / 2 == 256 * (T_PARSE / 32), "one 256-word span per warp");
-                uint32_t* wp = s_cnt32 + warp * 256 + lane;
-                uint32_t wv[8], pre[8], carry = 0;
+                static_assert(NBUCKET / 2 == 8 * T_PARSE, "two 16-byte vectors per thread");
+                uint4* v4 = reinterpret_cast<uint4*>(s_cnt32);
+                const uint4 va = v4[t], vb = v4[T_PARSE + t];
+                uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+                uint32_t sa = 0, sb = 0;
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    wv[r] = wp[r * 32];
-                    const uint32_t sum2 = (wv[r] & 0xffffu) + (wv[r] >> 16);
-                    uint32_t inc = sum2;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= (unsigned)o) inc += tt;
-                    }
-                    pre[r] = carry + inc - sum2;
-                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                for (int q = 0; q < 4; q++) {
+                    sa += (wa[q] & 0xffffu) + (wa[q] >> 16);
+                    sb += (wb[q] & 0xffffu) + (wb[q] >> 16);
                 }
-                if (lane == 0) sm->warp_tmp[warp] = carry;
+                const uint32_t packed = sa | (sb << 16);
+                uint32_t inc = packed;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (unsigned)o) inc += tt;
+                }
+                if (lane == 31) sm->warp_tmp[warp] = inc;
                 __syncthreads();
                 if (warp == 0) {
                     const uint32_t v = lane < nwarps ? sm->warp_tmp[lane] : 0u;
-                    uint32_t inc = v;
+                    uint32_t wi = v;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= (unsigned)o) inc += tt;
+                        const uint32_t tt = __shfl_up_sync(0xffffffffu, wi, o);
+                        if (lane >= (unsigned)o) wi += tt;
                     }
-                    sm->warp_tmp[lane] = inc - v;
-                    if (lane == 31) s_E[NBUCKET] = (uint16_t)inc;   // the entry past the last full word: everything before it
+                    sm->warp_tmp[lane] = wi - v;
+                    if (lane == 31) {
+                        sm->warp_tmp[32] = wi;
+                        s_E[NBUCKET] = (uint16_t)((wi & 0xffffu) + (wi >> 16));   // the entry past the last full word: everything before it
+                    }
                 }
                 __syncthreads();
-                const uint32_t base = sm->warp_tmp[warp];
+                const uint32_t ex = inc - packed + sm->warp_tmp[warp];
+                uint32_t ra = ex & 0xffffu, rb = (ex >> 16) + (sm->warp_tmp[32] & 0xffffu);
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const uint32_t e0 = base + pre[r];
-                    wp[r * 32] = e0 | ((e0 + (wv[r] & 0xffffu)) << 16);
+                for (int q = 0; q < 4; q++) {   // word = E[2k] | E[2k+1] << 16 -> run | (run + E[2k]) << 16
+                    const uint32_t ca = wa[q], cb = wb[q];
+                    wa[q] = ra * 0x10001u + (ca << 16);
+                    wb[q] = rb * 0x10001u + (cb << 16);
+                    ra += (ca & 0xffffu) + (ca >> 16);
+                    rb += (cb & 0xffffu) + (cb >> 16);
                 }
+                v4[t] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                v4[T_PARSE + t] = make_uint4(wb[0], wb[1], wb[2], wb[3]);
             }
             __syncthreads();
             PROF(2)
             // ---- P3: scatter tile by tile (cursors count up to the bucket ends): buckets end up
             //      ordered by position except inside a tile, then every bucket is put in order ----
+            if (t == 0) {   // sentinels of the fix-up's neighbour test: no tile holds position 0xFFFF
+                s_sorted[-1] = 0xFFFFu;
+                s_sorted[nh] = 0xFFFFu;
+            }
             for (uint32_t p0 = 0; p0 < nh; p0 += T) {
                 const uint32_t p = p0 + t;
                 if (p < nh) {
@@ -457,12 +507,10 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 uint32_t k = 0;
                 for (uint32_t ib = warp * 32; ib < nh; ib += T, k++) {   // warp-uniform trip count
                     const uint32_t i = ib + lane;
-                    bool cand = false;
-                    if (i < nh) {
-                        const uint32_t tile = (uint32_t)s_sorted[i] >> TILE_SHIFT;
-                        const uint32_t ql = i ? s_sorted[i - 1] : 0xffffffffu, qr = i + 1 < nh ? s_sorted[i + 1] : 0xffffffffu;
-                        cand = (ql >> TILE_SHIFT) == tile || (qr >> TILE_SHIFT) == tile;
-                    }
+                    // same tile <=> the positions differ only below the tile bits (sentinels at both ends; an index past
+                    // nh reads stale entries inside the array and is masked)
+                    const uint32_t pc = s_sorted[i], ql = s_sorted[(int)i - 1], qr = s_sorted[i + 1];
+                    const bool cand = i < nh && min(ql ^ pc, qr ^ pc) < (uint32_t)T_PARSE;
                     const uint32_t b = __ballot_sync(0xffffffffu, cand);
                     if (cand) {
                         const uint32_t slot = wcnt + __popc(b & ((1u << lane) - 1));
@@ -491,116 +539,184 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             //      preceding bytes differ starts a run: every position p+k inside it has a match of
             //      length end-(p+k) at the same distance, so only run heads are extended and
             //      best[p] = (prefix max over start positions of the run ends) - p  (P4c below).
-            //      Phase A, one lane per SORTED index (windows of 28 + 4 lanes of context), is a pure
-            //      screen: the four nearest own candidates are the four preceding lanes (their bytes
-            //      come by shuffle), the four nearest dictionary candidates come in one 16-byte bucket
-            //      record.  The surviving (position, source) pairs are compacted into a per-warp list and
-            //      extended 32 at a time (phase B), so the byte comparison runs with full warps instead
-            //      of the few lanes that happen to hold a candidate.
+            //      Phase A, one lane per SORTED index (windows of 32 - OWN lanes + OWN lanes of context), is a
+            //      pure screen: the nearest own candidates are the preceding lanes (their signatures come
+            //      by shuffle), the four nearest dictionary candidates come in one 16-byte bucket record.
+            //      The surviving (position, source) pairs are compacted slot by slot (one ballot each) into two
+            //      per-warp lists - own-chunk sources and dictionary sources - and extended 32 at a time
+            //      (phase B), so the byte comparison runs with full warps, from shared memory for the one
+            //      list and through the read-only path for the other.
             for (uint32_t i = t; i < n + (n >> 5); i += T) mptr[i] = 0;   // run keys: end << 15 | (32768 - dist)
             __syncthreads();
             {
                 const uint32_t* dictw = reinterpret_cast<const uint32_t*>(dict->bytes);
+                const uint4* bk4 = dict->bk4;
                 const bool use_dict = dlen != 0;
-                uint32_t* plist = s_cnt32 + warp * PAIR_CAP;   // the bucket table is dead: E is not needed to walk s_sorted
-                uint32_t pcnt = 0;                             // warp-uniform
+                // the bucket table is dead (E is not needed to walk s_sorted): its region holds the pair lists
+                // (lists are addressed by shared-window addresses: 32-bit arithmetic, one multiply-add per store)
+                const uint32_t olist = (uint32_t)__cvta_generic_to_shared(s_cnt32) + warp * 4u * (own_cap(OWN) + dict_cap(OWN));
+                const uint32_t dlist = olist + 4u * own_cap(OWN);
+                uint32_t otop = olist, dtop = dlist;           // list ends (warp-uniform)
+                const uint32_t lt = (1u << lane) - 1u;
                 const uint32_t nwin = (nh + WIN - 1) / WIN;
+                const int win_gap = (int)WSIZE - (int)dlen;    // a dictionary position q is inside the window of p iff q + win_gap >= p
+                const uint32_t* smem32 = reinterpret_cast<const uint32_t*>(smem);
                 struct StA { uint32_t sig; uint4 bk; };
-                // sig = 1 << 31 | tag << 23 | previous byte << 15 | position - the layout of a dictionary bucket record, with
-                // tag = eight bits of the hash product below the bucket bits; lanes outside the index range carry 0
-                auto stageA = [&](uint32_t w) {
-                    StA r;
-                    r.sig = 0; r.bk = make_uint4(0, 0, 0, 0);
+                // sig: the K-layout record of the lane's position (pos << 17 | valid | tag << 8 | previous byte); lanes
+                // outside the index range carry 0
+                // (the bucket record of a lane without a position keeps its old value: nothing reads it while sig == 0)
+                auto stageA = [&](uint32_t w, StA& r) {
+                    r.sig = 0;
                     const int i = (int)(WIN * w) - OWN + (int)lane;
                     // (a window past the last one only reads in-range context elements that nobody consumes)
                     if ((uint32_t)i < nh) {
                         const uint32_t p = s_sorted[i];
                         // bytes p-1 .. p+3 lie in two consecutive words: one pair of loads serves both the value and
-                        // the byte before it
-                        const uint32_t pm = p ? p - 1 : 0u;
-                        const uint32_t w0 = s_data32[pm >> 2], w1 = s_data32[(pm >> 2) + 1];
-                        const uint32_t sh8 = (pm & 3) * 8;
-                        const uint32_t lo5 = __funnelshift_r(w0, w1, sh8);                    // bytes pm .. pm+3
-                        const uint32_t v = p ? __funnelshift_r(lo5, w1 >> sh8, 8) : lo5;     // bytes p .. p+3
-                        r.sig = 0x80000000u | dict_tag23(v) | ((p ? (lo5 & 0xffu) : CHUNK_PREV0) << 15) | p;
-                        if (use_dict && lane >= OWN) r.bk = __ldg(&dict->bk4[hash_dict(v)]);
+                        // the byte before it (position 0 finds CHUNK_PREV0 in the pad before the chunk)
+                        const uint32_t off = p + (PAD_FRONT - 1);
+                        const uint32_t w0 = smem32[off >> 2], w1 = smem32[(off >> 2) + 1];
+                        const uint32_t o3 = off & 3u;
+                        const uint32_t v = __funnelshift_rc(w0, w1, o3 * 8u + 8u);   // bytes p .. p+3 (clamped shift: 32 -> w1)
+                        const uint32_t prod = v * 0x9E3779B1u;
+                        // byte 0 <- byte o3 of w0 (the previous byte), byte 1 <- byte 1 of the product (the tag)
+                        const uint32_t lowh = __byte_perm(w0, prod, o3 | 0x50u);
+                        r.sig = (lowh & 0xffffu) | (p * 0x20000u + K_VALID);
+                        if (use_dict && lane >= OWN) r.bk = __ldg(&bk4[prod >> (32 - DICT_HASH_BITS)]);
                     }
-                    return r;
                 };
-                auto extend_pairs = [&](uint32_t first, uint32_t count) {   // phase B on plist[first .. first+count)
+                // phase B: common prefix of chunk[p ..] and src[q ..], 8 bytes per step from three words a side
+                auto extend_own = [&](uint32_t first, uint32_t count) {
                     if (lane < count) {
-                        const uint32_t rec = plist[first + lane];
-                        const uint32_t p = rec & 0x7fffu, src = (rec >> 16) & 0x7fffu;
-                        const bool isd = (rec & 0x8000u) != 0;
-                        uint32_t lim = n - p, dist = p - src;
-                        const uint32_t* sw = s_data32;
-                        if (isd) {
-                            lim = min(lim, dlen - src);   // matches do not run from the dictionary into the chunk
-                            dist = p + dlen - src;
-                            sw = dictw;
+                        const uint32_t rec = lds_w(first + 4u * lane);
+                        const uint32_t p = rec & 0x7fffu, q = rec >> 17;
+#ifdef EXP_CAP_LIM
+                        const uint32_t lim = min(n - p, (uint32_t)EXP_CAP_LIM);
+#else
+                        const uint32_t lim = n - p;
+#endif
+                        const uint32_t sa = p * 8u, sb = q * 8u;   // funnel shifts take the amount modulo 32
+                        const uint32_t* A = s_data32 + (p >> 2);
+                        const uint32_t* B = s_data32 + (q >> 2);
+                        uint32_t a0 = A[0], b0 = B[0], l = 0;
+                        for (;;) {
+                            const uint32_t a1 = A[1], a2 = A[2], b1 = B[1], b2 = B[2];
+                            const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+                            if (x0) {
+                                l += (uint32_t)(__ffs((int)x0) - 1) >> 3;
+                                break;
+                            }
+                            const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+                            if (x1) {
+                                l += 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+                                break;
+                            }
+                            l += 8;
+                            if (l >= lim) break;
+                            a0 = a2; b0 = b2;
+                            A += 2; B += 2;
                         }
-                        const uint32_t l = extend_run(s_data32, sw, p, src, 0, lim);   // from 0: dictionary tags are only a filter
-                        if (l >= 4) atomicMax(&mptr[SK(p)], ((p + l) << 15) | (32768u - dist));
+                        l = min(l, lim);
+                        if (l >= 4) atomicMax(&mptr[SK(p)], ((p + l) << 15) | (32768u - (p - q)));
                     }
                 };
-                StA s0 = stageA(warp), s1 = stageA(warp + nwarps);
-                for (uint32_t w = warp; w < nwin; w += nwarps) {   // warp-uniform trip count
-                    const StA cur = s0;
-                    s0 = s1;
-                    s1 = stageA(w + 2 * nwarps);
-
-                    const int i = (int)(WIN * w) - OWN + (int)lane;
-                    const bool act = lane >= OWN && i < (int)nh;
-                    const uint32_t p = cur.sig & 0x7fffu;
-                    uint32_t rec[OWN + DICT_CAP];
-                    uint32_t mask = 0;
-                    // A candidate (own: the sig of a preceding lane; dictionary: a bucket record) starts a run here when
-                    // x = candidate ^ sig shows both valid, the same tag and a different previous byte, i.e.
-                    // 0x8000 <= x < 0x800000: one subtract and one compare.  The tag is only a filter (same bucket and
-                    // same tag, different bytes: 1 in 256): phase B compares the real bytes from the first one.
-                    // The pair record takes its source half straight from the candidate (bit 15 of that half is the low
-                    // bit of its previous byte and is masked off by the reader).
-#pragma unroll
-                    for (int d = 1; d <= OWN; d++) {
-                        const uint32_t sq = __shfl_up_sync(0xffffffffu, cur.sig, d);
-                        if (((sq ^ cur.sig) - 0x8000u) < 0x7F8000u) mask |= 1u << (d - 1);
-                        rec[d - 1] = __byte_perm(p, sq, 0x5410);
-                    }
-                    if (use_dict) {
-                        // inside the window  <=>  pos + WSIZE >= p + dlen
-                        const uint32_t pq = p | 0x8000u;
-                        const uint32_t thr = p + dlen > (uint32_t)WSIZE ? p + dlen - (uint32_t)WSIZE : 0u;
-                        const uint32_t c[4] = {cur.bk.x, cur.bk.y, cur.bk.z, cur.bk.w};
-#pragma unroll
-                        for (int u = 0; u < DICT_CAP; u++) {
-                            if (((c[u] ^ cur.sig) - 0x8000u) < 0x7F8000u && (c[u] & 0x7fffu) >= thr) mask |= (1u << OWN) << u;
-                            rec[OWN + u] = __byte_perm(pq, c[u], 0x5410);
+                auto extend_dict = [&](uint32_t first, uint32_t count) {
+                    if (lane < count) {
+                        const uint32_t rec = lds_w(first + 4u * lane);
+                        const uint32_t p = rec & 0x7fffu, q = rec >> 17;
+#ifdef EXP_CAP_LIM
+                        const uint32_t lim = min(min(n - p, dlen - q), (uint32_t)EXP_CAP_LIM);
+#else
+                        const uint32_t lim = min(n - p, dlen - q);   // matches do not run from the dictionary into the chunk
+#endif
+                        const uint32_t sa = p * 8u, sb = q * 8u;
+                        const uint32_t* A = s_data32 + (p >> 2);
+                        const uint32_t* B = dictw + (q >> 2);
+                        uint32_t a0 = A[0], b0 = __ldg(B), l = 0;
+                        for (;;) {
+                            const uint32_t a1 = A[1], a2 = A[2], b1 = __ldg(B + 1), b2 = __ldg(B + 2);
+                            const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+                            if (x0) {
+                                l += (uint32_t)(__ffs((int)x0) - 1) >> 3;
+                                break;
+                            }
+                            const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+                            if (x1) {
+                                l += 4 + ((uint32_t)(__ffs((int)x1) - 1) >> 3);
+                                break;
+                            }
+                            l += 8;
+                            if (l >= lim) break;
+                            a0 = a2; b0 = b2;
+                            A += 2; B += 2;
                         }
+                        l = min(l, lim);
+                        if (l >= 4) atomicMax(&mptr[SK(p)], ((p + l) << 15) | (32768u - (p + dlen - q)));
                     }
-                    if (!act) mask = 0;
-                    if (__any_sync(0xffffffffu, mask != 0)) {
-                        // compaction: exclusive scan of the per-lane pair counts
-                        const uint32_t c = __popc(mask);
-                        uint32_t inc = c;
+                };
+                // phase A on one staged window.  A candidate (own: the signature of a preceding lane; dictionary: a
+                // bucket record) starts a run here when k_head() holds - both valid, the same tag, a different previous
+                // byte; the tag is only a filter (same bucket and same tag, different bytes: 1 in 256): phase B compares
+                // the real bytes from the first one.
+                auto screen = [&](const StA& cur) {
+                    const uint32_t sig = cur.sig;
+                    const bool act = lane >= OWN && sig != 0;
+                    const uint32_t p = sig >> 17;
+                    // inside the window  <=>  pos + (WSIZE - dlen) >= p  <=>  record >= max(p - (WSIZE - dlen), 0) << 17
+                    const uint32_t thrK = (uint32_t)max((int)p - win_gap, 0) << 17;
+                    const uint32_t c[DICT_CAP] = {cur.bk.x, cur.bk.y, cur.bk.z, cur.bk.w};
+                    uint32_t sq[OWN];
+                    bool ho[OWN], hd[DICT_CAP];
+                    uint32_t bo[OWN], bd[DICT_CAP];
+                    // all tests first, then all ballots, then the stores: six independent chains
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
-                            if (lane >= (unsigned)o) inc += tt;
-                        }
-                        uint32_t o = pcnt + inc - c;
-#pragma unroll
-                        for (int sl = 0; sl < OWN + DICT_CAP; sl++)
-                            if ((mask >> sl) & 1u) plist[o++] = rec[sl];
-                        pcnt += __shfl_sync(0xffffffffu, inc, 31);
-                        __syncwarp();
-                        while (pcnt >= 32) {
-                            pcnt -= 32;
-                            extend_pairs(pcnt, 32);
-                        }
-                        __syncwarp();
+                    for (int d = 0; d < OWN; d++) {
+                        sq[d] = __shfl_up_sync(0xffffffffu, sig, d + 1);   // (a lane below d + 1 reads itself: never a head)
+                        ho[d] = act && k_head(sq[d], sig);
                     }
+#pragma unroll
+                    for (int u = 0; u < DICT_CAP; u++) hd[u] = act && c[u] >= thrK && k_head(c[u], sig);
+#pragma unroll
+                    for (int d = 0; d < OWN; d++) bo[d] = __ballot_sync(0xffffffffu, ho[d]);
+#pragma unroll
+                    for (int u = 0; u < DICT_CAP; u++) bd[u] = __ballot_sync(0xffffffffu, hd[u]);
+#pragma unroll
+                    for (int d = 0; d < OWN; d++) {
+                        sts_if(otop + 4u * __popc(bo[d] & lt), (sq[d] & K_POS) | p, ho[d]);
+                        otop += 4u * __popc(bo[d]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < DICT_CAP; u++) {
+                        sts_if(dtop + 4u * __popc(bd[u] & lt), (c[u] & K_POS) | p, hd[u]);
+                        dtop += 4u * __popc(bd[u]);
+                    }
+                    __syncwarp();
+                    while (otop - olist >= 128u) {
+                        otop -= 128u;
+                        extend_own(otop, 32);
+                    }
+                    while (dtop - dlist >= 128u) {
+                        dtop -= 128u;
+                        extend_dict(dtop, 32);
+                    }
+                    __syncwarp();
+                };
+                // two windows in flight per warp; each staged window is refilled right after it is consumed, so the
+                // staging registers never move
+                StA s0, s1;
+                s0.bk = s1.bk = make_uint4(0, 0, 0, 0);
+                stageA(warp, s0);
+                stageA(warp + nwarps, s1);
+                for (uint32_t w = warp; w < nwin;) {   // warp-uniform trip count
+                    screen(s0);
+                    stageA(w + 2 * nwarps, s0);
+                    w += nwarps;
+                    if (w >= nwin) break;
+                    screen(s1);
+                    stageA(w + 2 * nwarps, s1);
+                    w += nwarps;
                 }
-                if (pcnt) extend_pairs(0, pcnt);
+                if (otop != olist) extend_own(olist, (otop - olist) >> 2);
+                if (dtop != dlist) extend_dict(dlist, (dtop - dlist) >> 2);
             }
             __syncthreads();
             PROF(5)
@@ -1586,7 +1702,7 @@ __global__ void __launch_bounds__(1024) long_dict_kernel(DeflArgs a) {
             const uint32_t q1 = __ldcg(&w[i]);
             if (q1) {
                 const uint32_t q = q1 - 1;
-                w[i] = 0x80000000u | dict_tag23(le32(q)) | ((q ? (uint32_t)src[q - 1] : DICT_PREV0) << 15) | q;
+                w[i] = k_record(le32(q), q ? (uint32_t)src[q - 1] : DICT_PREV0, q);
             }
         }
         __syncthreads();
@@ -1719,7 +1835,7 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
         b.w = b.z;
         b.z = b.y;
         b.y = b.x;
-        b.x = 0x80000000u | dict_tag23(v) | ((j ? (uint32_t)tmp[j - 1] : DICT_PREV0) << 15) | j;
+        b.x = k_record(v, j ? (uint32_t)tmp[j - 1] : DICT_PREV0, j);
     }
     cudaError_t e = cudaMemcpyAsync(dev, img, sizeof(DictDev), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1730,9 +1846,9 @@ int ensure_dict(hmse_ctx* ctx, const uint8_t* d_zdict, uint32_t dict_len, uint32
     return HMSE_OK;
 }
 
-size_t parse_smem(uint32_t nmax, bool match_smem) {
-    return (size_t)nmax + 16 + 2 * (size_t)(nmax + nmax / 32) + CNT_WORDS * 4 + nmax / 16 +
-           ((sizeof(ParseSm) + 15) & ~15u) + (match_smem ? 4 * (size_t)(nmax + nmax / 32) : 0) + 64;
+size_t parse_smem(uint32_t nmax, bool match_smem, int own) {
+    return (size_t)PAD_FRONT + nmax + 16 + PAD_SORTED + 2 * (size_t)(nmax + nmax / 32) + cnt_words(own) * 4 + nmax / 16 +
+           ((sizeof(ParseSm) + 15) & ~15u) + (match_smem ? 4 * (size_t)(nmax + nmax / 32) : 0) + 32;
 }
 
 }  // namespace
@@ -1818,11 +1934,12 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     a.sizes = sizes;
     a.stat = d_stat;
 
-    const size_t sm_parse[N_CLASS] = {parse_smem(NMAX_SMALL, true), parse_smem(NMAX_MEDIUM, false), parse_smem(NMAX_LARGE, false)};
+    const size_t sm_parse[N_CLASS] = {parse_smem(NMAX_SMALL, true, OWN_SMALL), parse_smem(NMAX_MEDIUM, false, OWN_MEDIUM),
+                                      parse_smem(NMAX_LARGE, false, OWN_LARGE)};
     const size_t sm_huff = sizeof(HuffSm) * HUFF_WARPS;
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<RS_SMALL, OWN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[0]));
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5, OWN_MEDIUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[1]));
-    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5, OWN_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[2]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<RS_SMALL, OWN_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[0]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5, OWN_MEDIUM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[1]));
+    HMSE_CUDA(ctx, cudaFuncSetAttribute(parse_kernel<5, OWN_LARGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_parse[2]));
     HMSE_CUDA(ctx, cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_huff));
     const uint32_t nmax_c[N_CLASS] = {NMAX_SMALL, NMAX_MEDIUM, NMAX_LARGE};
     const uint32_t batch_c[N_CLASS] = {BATCH_SMALL, BATCH_MEDIUM, BATCH_LARGE};
@@ -1944,7 +2061,6 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
     for (int c = 0; c < N_CLASS; c++) {
         a.list = lists + (size_t)c * m;
         a.nmax = nmax_c[c];
-        a.match_smem = c == 0;
         for (uint32_t j0 = 0; j0 < n_class[c]; j0 += batch_c[c]) {
             a.job0 = j0;
             a.job1 = j0 + batch_c[c] < n_class[c] ? j0 + batch_c[c] : n_class[c];
@@ -1952,9 +2068,9 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             const uint32_t jobs = a.job1 - a.job0;
             KL(ctx);
             PARSE_EV(0);
-            if (c == 0) parse_kernel<RS_SMALL, OWN_SMALL><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
-            else if (c == 1) parse_kernel<5, OWN_MEDIUM><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
-            else parse_kernel<5, OWN_LARGE><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            if (c == 0) parse_kernel<RS_SMALL, OWN_SMALL, true><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            else if (c == 1) parse_kernel<5, OWN_MEDIUM, false><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
+            else parse_kernel<5, OWN_LARGE, false><<<jobs < ctas_c[c] ? jobs : ctas_c[c], T_PARSE, sm_parse[c], st>>>(a);
             PARSE_EV(1);
             if (level != 0) {
                 const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
@@ -1974,7 +2090,6 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
         la.chunk_nblk = (const uint32_t*)(ldev + off_nblk);
         la.stored_flag = ldev + off_flag;
         a.nmax = NMAX_LARGE;
-        a.match_smem = 0;
         a.list = (const uint32_t*)(ldev + off_jk);
         a.blk = (const uint32_t*)(ldev + off_jb);
         a.long_dicts = long_dicts;
@@ -1988,7 +2103,7 @@ HMSE_API int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0
             long_dict_kernel<<<jobs < (uint32_t)ctx->sm_count ? jobs : (uint32_t)ctx->sm_count, 1024, 0, st>>>(a);
             KL(ctx);
             PARSE_EV(0);
-            parse_kernel<5, OWN_LARGE><<<jobs < ctas_c[2] ? jobs : ctas_c[2], T_PARSE, sm_parse[2], st>>>(a);
+            parse_kernel<5, OWN_LARGE, false><<<jobs < ctas_c[2] ? jobs : ctas_c[2], T_PARSE, sm_parse[2], st>>>(a);
             PARSE_EV(1);
             const uint32_t hb = (jobs + HUFF_WARPS - 1) / HUFF_WARPS;
             KL(ctx);
