@@ -145,7 +145,10 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t hist[REC_WORDS];
     uint16_t bentry[32];
     uint32_t warp_tmp[40];
-    uint32_t job, pad0;
+    uint32_t job, blkno;        // the chunk (or block of a long chunk) being parsed: fetched by thread 0 while the
+    uint64_t cs, len;           //   previous one was parsed (job >= job1: none left)
+    uint64_t pf_cs;             // next chunk, announced early so that all threads can prefetch it into L2
+    uint32_t pf_len, pad0;
     uint32_t adler_a, adler_b;
 };
 
@@ -305,19 +308,43 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     // signature of a position needs no special case for p == 0; never overwritten
     if (t == 0) reinterpret_cast<uint32_t*>(smem)[PAD_FRONT / 4 - 1] = CHUNK_PREV0 << 24;
 
+    // Thread 0 fetches the descriptor of the NEXT chunk while the current one is parsed, one dependent global load per
+    // phase (work counter -> list -> selection -> cut points), so that a chunk starts without that chain of round trips;
+    // as soon as the next chunk's bytes are known every thread prefetches a share of them into L2.
+    uint32_t nx_job = 0, nx_k = 0, nx_blk = 0;
+    uint64_t nx_j = 0, nx_cs = 0, nx_len = 0;
+    auto next_job = [&](int step) {   // thread 0 only
+        if (step == 0) nx_job = a.job0 + atomicAdd(a.counter, 1u);
+        if (nx_job >= a.job1) return;
+        if (step == 1) {
+            nx_k = a.list[nx_job];
+            nx_blk = a.blk ? a.blk[nx_job] : 0u;
+        } else if (step == 2) {
+            nx_j = a.select ? a.select[nx_k] : (uint64_t)nx_k;
+        } else if (step == 3) {
+            nx_cs = nx_j ? a.cuts[nx_j - 1] : a.start0;
+            nx_len = a.cuts[nx_j] - nx_cs;
+        }
+    };
+    auto publish_job = [&]() {        // thread 0 only, after the last reader of the current descriptor
+        sm->job = nx_job;
+        sm->blkno = nx_blk;
+        sm->cs = nx_cs;
+        sm->len = nx_len;
+    };
+    if (t == 0) {
+        for (int st = 0; st < 4; st++) next_job(st);
+        publish_job();
+        sm->pf_len = 0;
+    }
     for (;;) {
-        __syncthreads();
-        if (t == 0) sm->job = a.job0 + atomicAdd(a.counter, 1u);
         __syncthreads();
         const uint32_t job = sm->job;
         if (job >= a.job1) break;
         long long tprev = clock64();
         const uint32_t bj = job - a.job0;  // index inside the batch
-        const uint32_t k = a.list[job];
-        const uint64_t j = a.select ? a.select[k] : (uint64_t)k;
-        uint64_t cs = j ? a.cuts[j - 1] : a.start0;
-        uint64_t len = a.cuts[j] - cs;
-        const uint32_t blkno = a.blk ? a.blk[job] : 0u;
+        uint64_t cs = sm->cs, len = sm->len;
+        const uint32_t blkno = sm->blkno;
         uint32_t rec_flags = 0;
         if (a.blk) {   // one block of a long chunk
             rec_flags = REC_MULTI | ((uint64_t)(blkno + 1) * LONG_BLOCK >= len ? REC_LAST : 0u);
@@ -334,23 +361,70 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
         //      taken from the words in flight (byte sum and position-weighted byte sum of a word are one
         //      instruction each), clear tables ---------------------------------------------------------
         {
-            const uint32_t kmis = (uint32_t)((uintptr_t)src & 3);
-            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(src - kmis);
             const uint32_t nw = (n + 3) >> 2;
             uint32_t sa = 0, sb = 0;   // sb <= 16 words x 32768 x 1020 per thread: no overflow
-            for (uint32_t i = t; i < nw + 4 && i < (nmax + 16) / 4; i += T) {
-                uint32_t v = 0;
-                if (i < nw) {
-                    uint32_t lo = __ldg(wsrc + i);
-                    uint32_t hi = kmis ? __ldg(wsrc + i + 1) : 0u;
-                    v = __funnelshift_r(lo, hi, kmis * 8);
-                    const uint32_t rem = n - 4 * i;  // bytes of this word inside the chunk
-                    if (rem < 4) v &= (1u << (8 * rem)) - 1;
-                    const uint32_t bs = __vsadu4(v, 0u);
-                    sa += bs;
-                    sb += (n - 4 * i) * bs - __dp4a(v, 0x03020100u, 0u);   // sum over bytes of (n - position) * byte
+            auto sums = [&](uint32_t v, uint32_t wi) {   // Adler-32 partial sums of chunk word wi (already masked to the chunk)
+                const uint32_t bs = __vsadu4(v, 0u);
+                sa += bs;
+                sb += (n - 4 * wi) * bs - __dp4a(v, 0x03020100u, 0u);   // sum over bytes of (n - position) * byte
+            };
+            const uint32_t mis = (uint32_t)((uintptr_t)src & 15);
+            if (src - mis >= a.data) {
+                // 16-byte vectors: every thread has all its loads in flight at once (two vectors of the chunk, each
+                // assembled from the aligned vector it starts in and the next one), so the stage costs one memory round
+                // trip instead of one per 4-byte word.  Source vector j holds bytes of the chunk iff j < nsrc: the last
+                // one ends within the 16 bytes of slack the interface asks for.
+                const uint4* vsrc = reinterpret_cast<const uint4*>(src - mis);
+                const uint32_t nsrc = (n + mis + 15) >> 4;
+                const uint32_t nvec = min((nw + 4 + 3) >> 2, (nmax + 16) / 16);   // output vectors, zero slack included
+                const uint32_t q = mis >> 2, sh = (mis & 3) * 8;
+                uint4* dst = reinterpret_cast<uint4*>(s_data32);
+                auto emit = [&](uint32_t iv, const uint4& A, const uint4& B) {
+                    const uint32_t s8[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+                    uint32_t u[7], w[5], o[4];
+#pragma unroll
+                    for (int k = 0; k < 7; k++) u[k] = (q & 1) ? s8[k + 1] : s8[k];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) w[k] = (q & 2) ? u[k + 2] : u[k];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t wi = 4 * iv + k;
+                        uint32_t v = __funnelshift_r(w[k], w[k + 1], sh);
+                        if (wi >= nw) v = 0;
+                        else if (n - 4 * wi < 4) v &= (1u << (8 * (n - 4 * wi))) - 1;
+                        sums(v, wi);
+                        o[k] = v;
+                    }
+                    dst[iv] = make_uint4(o[0], o[1], o[2], o[3]);
+                };
+                const uint4 z4 = make_uint4(0, 0, 0, 0);
+                for (uint32_t iv = t; iv < nvec; iv += 2 * T) {
+                    const uint32_t iv1 = iv + T;
+                    uint4 A0 = z4, B0 = z4, A1 = z4, B1 = z4;
+                    if (iv < nsrc) A0 = __ldg(vsrc + iv);
+                    if (mis && iv + 1 < nsrc) B0 = __ldg(vsrc + iv + 1);
+                    if (iv1 < nvec) {
+                        if (iv1 < nsrc) A1 = __ldg(vsrc + iv1);
+                        if (mis && iv1 + 1 < nsrc) B1 = __ldg(vsrc + iv1 + 1);
+                    }
+                    emit(iv, A0, B0);
+                    if (iv1 < nvec) emit(iv1, A1, B1);
                 }
-                s_data32[i] = v;
+            } else {   // a first chunk less than 16 bytes into a buffer that is only 4-byte aligned: word loads
+                const uint32_t kmis = mis & 3;
+                const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(src - kmis);
+                for (uint32_t i = t; i < nw + 4 && i < (nmax + 16) / 4; i += T) {
+                    uint32_t v = 0;
+                    if (i < nw) {
+                        uint32_t lo = __ldg(wsrc + i);
+                        uint32_t hi = kmis ? __ldg(wsrc + i + 1) : 0u;
+                        v = __funnelshift_r(lo, hi, kmis * 8);
+                        const uint32_t rem = n - 4 * i;  // bytes of this word inside the chunk
+                        if (rem < 4) v &= (1u << (8 * rem)) - 1;
+                        sums(v, i);
+                    }
+                    s_data32[i] = v;
+                }
             }
             for (uint32_t i = t; i < CNT_WORDS; i += T) s_cnt32[i] = 0;   // (the bucket table proper: the rest of the region only holds pair lists)
             for (uint32_t i = t; i < REC_WORDS; i += T) sm->hist[i] = 0;
@@ -373,6 +447,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
         }
         __syncthreads();
         PROF(0)
+        if (t == 0 && a.level != 0) next_job(0);
         const uint32_t nh = n >= 4 ? n - 3 : 0;  // hashed positions
         PROF(1)
         uint32_t n_words = 0;
@@ -450,91 +525,87 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             }
             __syncthreads();
             PROF(2)
-            // ---- P3: scatter tile by tile (cursors count up to the bucket ends): buckets end up
-            //      ordered by position except inside a tile, then every bucket is put in order ----
-            if (t == 0) {   // sentinels of the fix-up's neighbour test: no tile holds position 0xFFFF
-                s_sorted[-1] = 0xFFFFu;
-                s_sorted[nh] = 0xFFFFu;
-            }
-            for (uint32_t p0 = 0; p0 < nh; p0 += T) {
-                const uint32_t p = p0 + t;
-                if (p < nh) {
-                    const uint32_t h1 = (uint32_t)s_h16[p] + 1;
-                    const uint32_t sh = 16 * (h1 & 1);
-                    const uint32_t old = atomicAdd(&s_cnt32[h1 >> 1], 1u << sh);
-                    s_sorted[(old >> sh) & 0xffffu] = (uint16_t)p;
-                }
-                __syncthreads();
-            }
-            PROF(3)
-            // Buckets are already ordered except for same-hash positions that were scattered in the same
-            // tile (common in text: a word repeated within 512 bytes).  Such a group is contiguous in the
-            // bucket.  Pass 1 (all elements, cheap): an element whose neighbours both come from other tiles is in
-            // place; the others are compacted into a list.  Pass 2 (dense over the list): a listed element finds
-            // its rank inside its group (a neighbour belongs to the same bucket iff its stored hash agrees; groups
-            // are tiny) and writes itself to a temporary copy.  Pass 3 copies the moved elements back.
-            uint16_t* s_tmp16 = reinterpret_cast<uint16_t*>(mptr);   // match words are not written before P4
-            uint16_t* s_list = s_E;                                    // the cursors are dead; bit 15 = "moved"
-            constexpr uint32_t LIST_CAP = CNT_WORDS * 2;
-            uint64_t moved = 0;   // elements handled in line because the list was full: bit k = index t' + k*T moved
-            auto fix_member = [&](uint32_t i) -> bool {
-                const uint32_t p = s_sorted[i];
-                const uint32_t tile = p >> TILE_SHIFT;
-                const uint32_t h = s_h16[p];
-                uint32_t first = i, smaller = 0, others = 0;
-                for (uint32_t j = i; j > 0;) {   // left neighbours of the same tile and bucket
-                    j--;
-                    const uint32_t q = s_sorted[j];
-                    if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
-                    first = j;
-                    smaller += q < p;
-                    others++;
-                }
-                for (uint32_t j = i + 1; j < nh; j++) {
-                    const uint32_t q = s_sorted[j];
-                    if ((q >> TILE_SHIFT) != tile || s_h16[q] != h) break;
-                    smaller += q < p;
-                    others++;
-                }
-                if (others) s_tmp16[first + smaller] = (uint16_t)p;
-                return others != 0;
-            };
-            // every warp keeps its own list (a shared list head would serialise the sixteen warps on one atomic)
-            constexpr uint32_t WCAP = LIST_CAP / (T_PARSE / 32);
-            uint16_t* wlist = s_list + warp * WCAP;
+            if (t == 0) next_job(1);
+            // ---- P3: scatter tile by tile (cursors count up to the bucket ends): buckets end up ordered by position
+            //      except for same-hash positions that were scattered in the same tile (common in text: a word repeated
+            //      within 512 bytes).  Such a group is contiguous in the bucket, and it is complete at the barrier that
+            //      ends its tile: in the next trip every thread looks at the slot to the right of the one it filled - a
+            //      position of the same tile there (same tile <=> the two differ only below the tile bits) makes the slot
+            //      a candidate for the fix-up below.  The test runs in the shadow of the next tile's atomic; a slot the
+            //      chunk has not filled yet holds a stale position, which at worst adds a candidate.
+            uint16_t* wlist = reinterpret_cast<uint16_t*>(mptr) + warp * (nmax / 16);   // <= 32 candidates per tile and warp
             uint32_t wcnt = 0;   // warp-uniform
             {
-                uint32_t k = 0;
-                for (uint32_t ib = warp * 32; ib < nh; ib += T, k++) {   // warp-uniform trip count
-                    const uint32_t i = ib + lane;
-                    // same tile <=> the positions differ only below the tile bits (sentinels at both ends; an index past
-                    // nh reads stale entries inside the array and is masked)
-                    const uint32_t pc = s_sorted[i], ql = s_sorted[(int)i - 1], qr = s_sorted[i + 1];
-                    const bool cand = i < nh && min(ql ^ pc, qr ^ pc) < (uint32_t)T_PARSE;
-                    const uint32_t b = __ballot_sync(0xffffffffu, cand);
-                    if (cand) {
-                        const uint32_t slot = wcnt + __popc(b & ((1u << lane) - 1));
-                        if (slot < WCAP) wlist[slot] = (uint16_t)i;
-                        else if (fix_member(i)) moved |= 1ull << k;   // (only on highly repetitive chunks)
+                if (t == 0) s_sorted[nh] = 0xFFFFu;   // no tile holds position 0xFFFF
+                const uint32_t lt = (1u << lane) - 1u;
+                uint32_t chk_slot = 0xffffffffu, chk_p = 0;
+                for (uint32_t p0 = 0; p0 < nh + T; p0 += T) {   // the last trip only looks at the last tile
+                    const uint32_t p = p0 + t;
+                    uint32_t old = 0, sh = 0;
+                    if (p < nh) {
+                        const uint32_t h1 = (uint32_t)s_h16[p] + 1;
+                        sh = 16 * (h1 & 1);
+                        old = atomicAdd(&s_cnt32[h1 >> 1], 1u << sh);
                     }
+                    const bool cand = chk_slot != 0xffffffffu && ((uint32_t)s_sorted[chk_slot + 1] ^ chk_p) < (uint32_t)T_PARSE;
+                    const uint32_t b = __ballot_sync(0xffffffffu, cand);
+                    if (cand) wlist[wcnt + __popc(b & lt)] = (uint16_t)chk_slot;
                     wcnt += __popc(b);
+                    chk_slot = 0xffffffffu;
+                    if (p < nh) {
+                        chk_slot = (old >> sh) & 0xffffu;
+                        chk_p = p;
+                        s_sorted[chk_slot] = (uint16_t)p;
+                    }
+                    __syncthreads();
                 }
             }
-            __syncwarp();
-            const uint32_t n_list = wcnt < WCAP ? wcnt : WCAP;
-            for (uint32_t j = lane; j < n_list; j += 32)
-                if (fix_member(wlist[j])) wlist[j] |= 0x8000u;
-            __syncthreads();   // every group has been read before any element moves
-            for (uint32_t j = lane; j < n_list; j += 32) {
-                const uint32_t e = wlist[j];
-                if (e & 0x8000u) s_sorted[e & 0x7fffu] = s_tmp16[e & 0x7fffu];
-            }
-            for (uint64_t mm = moved; mm; mm &= mm - 1) {
-                const uint32_t i = warp * 32 + lane + (uint32_t)(__ffsll((long long)mm) - 1) * T;
-                s_sorted[i] = s_tmp16[i];
+            PROF(3)
+            if (t == 0) next_job(2);
+            // ---- P3b: the element in the FIRST slot of a group (a neighbour belongs to the same bucket iff its stored hash
+            //      agrees) sorts the whole group in place - groups are tiny, and one thread per group means no temporary
+            //      copy: whatever a concurrent reader finds in a slot of a group that is being sorted is some member of that
+            //      group, which has the tile and the bucket the reader tests for.
+            {
+                auto sort_group = [&](uint32_t i) {   // i: a candidate slot
+                    const uint32_t p = s_sorted[i], r = s_sorted[i + 1];
+                    const uint32_t h = s_h16[p];
+                    if ((r ^ p) >= (uint32_t)T_PARSE || s_h16[r] != h) return;          // another tile, or the next bucket
+                    if (i) {
+                        const uint32_t l = s_sorted[i - 1];
+                        if ((l ^ p) < (uint32_t)T_PARSE && s_h16[l] == h) return;       // not the first slot of its group
+                    }
+                    uint32_t g = 2;
+                    for (;; g++) {                                                        // (the sentinel at nh ends the last group)
+                        const uint32_t q = s_sorted[i + g];
+                        if ((q ^ p) >= (uint32_t)T_PARSE || s_h16[q] != h) break;
+                    }
+                    for (uint32_t x = 1; x < g; x++) {                                    // insertion sort of g (mostly 2) positions
+                        const uint32_t v = s_sorted[i + x];
+                        uint32_t y = x;
+                        for (; y > 0; y--) {
+                            const uint32_t u = s_sorted[i + y - 1];
+                            if (u < v) break;
+                            s_sorted[i + y] = (uint16_t)u;
+                        }
+                        s_sorted[i + y] = (uint16_t)v;
+                    }
+                };
+                __syncwarp();
+                for (uint32_t j = lane; j < wcnt; j += 32) sort_group(wlist[j]);
             }
             __syncthreads();
             PROF(4)
+            if (t == 0) {   // the next chunk's bytes are known: announce them for the L2 prefetch below
+                next_job(3);
+                uint64_t pc = nx_cs, pl = nx_len;
+                if (a.blk) {
+                    pc += (uint64_t)nx_blk * LONG_BLOCK;
+                    pl = pl - (uint64_t)nx_blk * LONG_BLOCK < LONG_BLOCK ? pl - (uint64_t)nx_blk * LONG_BLOCK : LONG_BLOCK;
+                }
+                sm->pf_cs = pc;
+                sm->pf_len = nx_job < a.job1 ? (uint32_t)pl : 0u;
+            }
             // ---- P4: matches as RUNS.  A pair (position p, source q) whose four bytes agree and whose
             //      preceding bytes differ starts a run: every position p+k inside it has a match of
             //      length end-(p+k) at the same distance, so only run heads are extended and
@@ -548,6 +619,11 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             //      list and through the read-only path for the other.
             for (uint32_t i = t; i < n + (n >> 5); i += T) mptr[i] = 0;   // run keys: end << 15 | (32768 - dist)
             __syncthreads();
+            {   // the next chunk, one 128-byte line per thread: in L2 by the time its P0 runs
+                const uint32_t pl = sm->pf_len;
+                const uint8_t* pb = a.data + sm->pf_cs;
+                for (uint32_t o = t * 128u; o < pl; o += T * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
+            }
             {
                 const uint32_t* dictw = reinterpret_cast<const uint32_t*>(dict->bytes);
                 const uint4* bk4 = dict->bk4;
@@ -884,6 +960,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             rec.bits = 0;
             rec.pad = 0;
             a.recs[bj] = rec;
+            if (a.level == 0)
+                for (int st = 0; st < 4; st++) next_job(st);
+            publish_job();
             atomicAdd(&a.stat[0], (unsigned long long)n_words);
             atomicAdd(&a.stat[1], (unsigned long long)n);
             atomicAdd(&a.stat[2], 1ull);
