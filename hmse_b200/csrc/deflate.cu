@@ -267,6 +267,20 @@ __device__ __forceinline__ uint32_t lds_w(uint32_t saddr) {
     return v;
 }
 
+// Global loads with an L1 policy.  Two CTAs of the small class leave the SM about 28 KB of L1: the dictionary TEXT (<= 32 KB,
+// read by every extension step) should live there, so the loads that would wash it out do not allocate - the 512 KB of
+// bucket records (one random 16-byte record per position) and the chunk bytes (read once).
+__device__ __forceinline__ uint4 ldg_stream4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // Match word: bits 16..24 length (0 = literal), bit 15 "lazy: emit as literal", bits 0..14 distance-1.
 __device__ __forceinline__ bool mw_is_match(uint32_t mw) { return (mw >> 16) != 0 && !(mw & 0x8000u); }
 
@@ -401,11 +415,11 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 for (uint32_t iv = t; iv < nvec; iv += 2 * T) {
                     const uint32_t iv1 = iv + T;
                     uint4 A0 = z4, B0 = z4, A1 = z4, B1 = z4;
-                    if (iv < nsrc) A0 = __ldg(vsrc + iv);
-                    if (mis && iv + 1 < nsrc) B0 = __ldg(vsrc + iv + 1);
+                    if (iv < nsrc) A0 = ldg_stream4(vsrc + iv);
+                    if (mis && iv + 1 < nsrc) B0 = ldg_stream4(vsrc + iv + 1);
                     if (iv1 < nvec) {
-                        if (iv1 < nsrc) A1 = __ldg(vsrc + iv1);
-                        if (mis && iv1 + 1 < nsrc) B1 = __ldg(vsrc + iv1 + 1);
+                        if (iv1 < nsrc) A1 = ldg_stream4(vsrc + iv1);
+                        if (mis && iv1 + 1 < nsrc) B1 = ldg_stream4(vsrc + iv1 + 1);
                     }
                     emit(iv, A0, B0);
                     if (iv1 < nvec) emit(iv1, A1, B1);
@@ -657,7 +671,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         // byte 0 <- byte o3 of w0 (the previous byte), byte 1 <- byte 1 of the product (the tag)
                         const uint32_t lowh = __byte_perm(w0, prod, o3 | 0x50u);
                         r.sig = (lowh & 0xffffu) | (p * 0x20000u + K_VALID);
-                        if (use_dict && lane >= OWN) r.bk = __ldg(&bk4[prod >> (32 - DICT_HASH_BITS)]);
+                        if (use_dict && lane >= OWN) r.bk = ldg_stream4(&bk4[prod >> (32 - DICT_HASH_BITS)]);
                     }
                 };
                 // phase B: common prefix of chunk[p ..] and src[q ..], 8 bytes per step from three words a side
@@ -707,9 +721,9 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         const uint32_t sa = p * 8u, sb = q * 8u;
                         const uint32_t* A = s_data32 + (p >> 2);
                         const uint32_t* B = dictw + (q >> 2);
-                        uint32_t a0 = A[0], b0 = __ldg(B), l = 0;
+                        uint32_t a0 = A[0], b0 = ldg_keep(B), l = 0;
                         for (;;) {
-                            const uint32_t a1 = A[1], a2 = A[2], b1 = __ldg(B + 1), b2 = __ldg(B + 2);
+                            const uint32_t a1 = A[1], a2 = A[2], b1 = ldg_keep(B + 1), b2 = ldg_keep(B + 2);
                             const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
                             if (x0) {
                                 l += (uint32_t)(__ffs((int)x0) - 1) >> 3;
