@@ -1466,30 +1466,34 @@ struct Emitter {
     }
 };
 
-// Bit string of token word w (prev = the word before it): value and length (<= 28 bits).
-__device__ __forceinline__ void word_bits(const uint32_t* codes, uint32_t w, uint32_t prev, uint32_t& val, uint32_t& nb) {
-    uint32_t sy, eb, ev, c;
-    if (prev & 0x8000u) {            // distance word of a match
-        dist_sym(w + 1, sy, eb, ev);
-        c = codes[288 + sy];
-    } else if (w & 0x8000u) {        // length word of a match
-        len_sym(w & 0x1ffu, sy, eb, ev);
-        c = codes[sy];
-    } else {                         // literal
-        c = codes[w];
-        eb = 0;
-        ev = 0;
-    }
-    const uint32_t cl = c >> 16;
-    val = (c & 0xffffu) | (ev << cl);
+// Bit strings of the token words.  Literals and match lengths come from a per-block table s_tab[512] of packed entries
+// (value | bits << 27: a literal's code, or a length's code with its extra bits already appended - 20 bits at most), built
+// once per block; distance words are computed (30 symbols from a logarithm) without a branch.  Every lane runs the same
+// instructions whatever kind of word it holds: the loop used to serialise three divergent paths per step.
+__device__ __forceinline__ uint32_t tab_index(uint32_t w) {   // literal 0..255 -> itself; length word 0x8000 | len -> 253 + len
+    return (w & 0x8000u) ? 253u + (w & 0x1ffu) : w;
+}
+__device__ __forceinline__ void dist_bits(const uint32_t* codes, uint32_t d, uint32_t& val, uint32_t& nb) {   // d = distance - 1
+    const uint32_t eb = (uint32_t)(31 - __clz((int)(d | 2u))) - 1u;       // 0 for d < 4
+    const uint32_t sy = d < 4 ? d : 2 * eb + 2 + ((d >> eb) & 1u);
+    const uint32_t c = codes[288 + sy], cl = c >> 16;
+    val = (c & 0xffffu) | ((d & ((1u << eb) - 1u)) << cl);
     nb = cl + eb;
+}
+__device__ __forceinline__ void word_bits(const uint32_t* codes, const uint32_t* tab, uint32_t w, bool is_dist, uint32_t& val,
+                                          uint32_t& nb) {
+    const uint32_t e = tab[is_dist ? 0u : tab_index(w)];
+    uint32_t dv, dn;
+    dist_bits(codes, is_dist ? w : 0u, dv, dn);
+    val = is_dist ? dv : (e & 0x7ffffffu);
+    nb = is_dist ? dn : (e >> 27);
 }
 
 // Emits one coded block (mode 1 or 2) of batch job bj at bit offset bit0 of the stream words out32, which the
 // caller has zeroed (words shared by two writers are OR-ed).  Collective over the CTA; returns the bit offset
 // after the end-of-block code.
 __device__ uint32_t emit_block(const DeflArgs& a, uint32_t bj, const ChunkRec& rec, uint32_t* out32, uint32_t bit0,
-                               uint32_t* s_codes, uint32_t* s_tmp, uint32_t* s_hdr) {
+                               uint32_t* s_codes, uint32_t* s_tmp, uint32_t* s_hdr, uint32_t* s_tab) {
     const uint32_t T = T_ENCODE, t = threadIdx.x;
     __syncthreads();
     for (uint32_t i = t; i < REC_WORDS; i += T) s_codes[i] = a.hist[(size_t)bj * REC_WORDS + i];
@@ -1501,20 +1505,40 @@ __device__ uint32_t emit_block(const DeflArgs& a, uint32_t bj, const ChunkRec& r
         uint8_t* sh = reinterpret_cast<uint8_t*>(s_hdr);
         for (uint32_t i = t; i < hbytes; i += T) sh[i] = gh[i];
     }
+    for (uint32_t i = t; i < 512; i += T) {   // the table: literal i, or match length i - 253
+        uint32_t c, eb = 0, ev = 0;
+        if (i < 256) {
+            c = s_codes[i];
+        } else {
+            uint32_t sy;
+            len_sym(i - 253, sy, eb, ev);
+            c = s_codes[sy];
+        }
+        const uint32_t cl = c >> 16;
+        s_tab[i] = (c & 0xffffu) | (ev << cl) | ((cl + eb) << 27);
+    }
+    __syncthreads();
     const uint16_t* tk = a.tokens + (size_t)bj * a.nmax;
     const uint32_t W = rec.n_words;
     const uint32_t per = (W + T - 1) / T;
     const uint32_t w0 = t * per < W ? t * per : W, w1 = w0 + per < W ? w0 + per : W;
+    // the word before a thread's first one is a length word (so that the first one is a distance) iff it carries the flag
+    // and is not itself a distance: a distance (<= 32767) never carries it, so only a length word before IT can mislead
+    bool dist0 = false;
+    if (w0) {
+        const uint32_t p1 = tk[w0 - 1];
+        dist0 = (p1 & 0x8000u) != 0;
+        if (dist0 && w0 >= 2 && (tk[w0 - 2] & 0x8000u)) dist0 = false;   // (cannot happen: kept as the old code had it)
+    }
     uint32_t bits = 0;
     {
-        uint32_t prev = w0 ? tk[w0 - 1] : 0u;
-        if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;  // prev is itself a distance word
+        bool is_dist = dist0;
         for (uint32_t i = w0; i < w1; i++) {
             const uint32_t w = tk[i];
             uint32_t val, nb;
-            word_bits(s_codes, w, prev, val, nb);
+            word_bits(s_codes, s_tab, w, is_dist, val, nb);
             bits += nb;
-            prev = (prev & 0x8000u) ? 0u : w;  // a distance word never introduces another one
+            is_dist = !is_dist && (w & 0x8000u);   // a distance word never introduces another one
         }
     }
     uint32_t tok_bits;
@@ -1531,14 +1555,13 @@ __device__ uint32_t emit_block(const DeflArgs& a, uint32_t bj, const ChunkRec& r
     Emitter em;
     em.begin(out32, my_off);
     {
-        uint32_t prev = w0 ? tk[w0 - 1] : 0u;
-        if (w0 >= 2 && (prev & 0x8000u) && (tk[w0 - 2] & 0x8000u)) prev = 0;
+        bool is_dist = dist0;
         for (uint32_t i = w0; i < w1; i++) {
             const uint32_t w = tk[i];
             uint32_t val, nb;
-            word_bits(s_codes, w, prev, val, nb);
+            word_bits(s_codes, s_tab, w, is_dist, val, nb);
             em.put(val, nb);
-            prev = (prev & 0x8000u) ? 0u : w;
+            is_dist = !is_dist && (w & 0x8000u);
         }
     }
     em.end();
@@ -1570,6 +1593,7 @@ __global__ void __launch_bounds__(T_ENCODE) encode_kernel(DeflArgs a) {
     __shared__ uint32_t s_codes[REC_WORDS];
     __shared__ uint32_t s_tmp[40];
     __shared__ uint32_t s_hdr[160];
+    __shared__ uint32_t s_tab[512];
     const uint32_t T = T_ENCODE, t = threadIdx.x;
     const uint32_t n_jobs = a.job1 - a.job0;
     for (uint32_t bj = blockIdx.x; bj < n_jobs; bj += gridDim.x) {
@@ -1587,7 +1611,7 @@ __global__ void __launch_bounds__(T_ENCODE) encode_kernel(DeflArgs a) {
             // zero the deflate words (+ trailer spill) so shared boundary words can be OR-ed
             const uint32_t zw = (body + 4 + 3) >> 2;
             for (uint32_t i = t; i < zw; i += T) out32[i] = 0;
-            emit_block(a, bj, rec, out32, 0, s_codes, s_tmp, s_hdr);
+            emit_block(a, bj, rec, out32, 0, s_codes, s_tmp, s_hdr, s_tab);
             __syncthreads();
             if (t == 0) put_be32(slot + 2 + hdr_len + body, rec.adler);
         } else {
@@ -1626,6 +1650,7 @@ __global__ void __launch_bounds__(T_ENCODE) encode_long_kernel(DeflArgs a, LongA
     __shared__ uint32_t s_codes[REC_WORDS];
     __shared__ uint32_t s_tmp[40];
     __shared__ uint32_t s_hdr[160];
+    __shared__ uint32_t s_tab[512];
     const uint32_t T = T_ENCODE, t = threadIdx.x;
     for (uint32_t ci = la.c0 + blockIdx.x; ci < la.c1; ci += gridDim.x) {
         __syncthreads();
@@ -1648,7 +1673,7 @@ __global__ void __launch_bounds__(T_ENCODE) encode_long_kernel(DeflArgs a, LongA
         uint32_t bit = 0, ad_a = 1, ad_b = 0;
         for (uint32_t b = 0; b < nblk; b++) {
             const ChunkRec rec = a.recs[bj0 + b];
-            bit = emit_block(a, bj0 + b, rec, out32, bit, s_codes, s_tmp, s_hdr);
+            bit = emit_block(a, bj0 + b, rec, out32, bit, s_codes, s_tmp, s_hdr, s_tab);
             // Adler-32 of a concatenation (zlib's adler32_combine)
             const uint32_t a2 = rec.adler & 0xffffu, b2 = rec.adler >> 16;
             const uint32_t rem = rec.n % 65521u;
