@@ -149,6 +149,8 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
     uint64_t cs, len;           //   previous one was parsed (job >= job1: none left)
     uint64_t pf_cs;             // next chunk, announced early so that all threads can prefetch it into L2
     uint32_t pf_len, pad0;
+    uint32_t nx_job, nx_k, nx_blk, pad1;   // the descriptor being fetched (thread 0's state: kept here, not in registers
+    uint64_t nx_j, nx_cs, nx_len;          //   that every thread would carry through all phases)
     uint32_t adler_a, adler_b;
 };
 
@@ -170,8 +172,9 @@ __device__ __forceinline__ uint32_t ldg32u(const uint8_t* base, uint32_t off) {
     return __funnelshift_r(__ldg(w), __ldg(w + 1), (off & 3) * 8);
 }
 
-// Exclusive scan of one u32 per thread; *total = block sum (same value in every thread).
-// tmp = 33 words of shared memory.
+// Exclusive scan of one u32 per thread; *total = block sum (same value in every thread).  tmp = 32 words of shared
+// memory.  ONE barrier: every warp folds the totals of the warps before it by itself (a REDUX) instead of waiting for a
+// scan by warp 0 and two more barriers.  The caller keeps a barrier between two uses of the same tmp.
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, uint32_t* total) {
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t inc = v;
@@ -180,27 +183,14 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, u
         uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= (unsigned)o) inc += t;
     }
-    __syncthreads();
     if (lane == 31) tmp[w] = inc;
     __syncthreads();
-    if (w == 0) {
-        uint32_t s = lane < nw ? tmp[lane] : 0, si = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
-            if (lane >= (unsigned)o) si += t;
-        }
-        tmp[lane] = si - s;
-        if (lane == 31) tmp[32] = si;  // zeros past nw: lane 31 holds the grand total
-    }
-    __syncthreads();
-    const uint32_t r = inc - v + tmp[w];
-    *total = tmp[32];
-    __syncthreads();
-    return r;
+    const uint32_t tv = lane < nw ? tmp[lane] : 0u;
+    *total = __reduce_add_sync(0xffffffffu, tv);
+    return inc - v + __reduce_add_sync(0xffffffffu, lane < w ? tv : 0u);
 }
 
-// Exclusive prefix MAX of one u32 per thread (identity 0).  tmp = 33 words of shared memory.
+// Exclusive prefix MAX of one u32 per thread (identity 0), same scheme.
 __device__ __forceinline__ uint32_t block_excl_scan_max(uint32_t v, uint32_t* tmp) {
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t inc = v;
@@ -211,25 +201,10 @@ __device__ __forceinline__ uint32_t block_excl_scan_max(uint32_t v, uint32_t* tm
     }
     uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) exc = 0;
-    __syncthreads();
     if (lane == 31) tmp[w] = inc;
     __syncthreads();
-    if (w == 0) {
-        const uint32_t s = lane < nw ? tmp[lane] : 0;
-        uint32_t si = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
-            if (lane >= (unsigned)o) si = max(si, t);
-        }
-        uint32_t se = __shfl_up_sync(0xffffffffu, si, 1);
-        if (lane == 0) se = 0;
-        tmp[lane] = se;
-    }
-    __syncthreads();
-    const uint32_t r = max(exc, tmp[w]);
-    __syncthreads();
-    return r;
+    const uint32_t tv = lane < nw && lane < w ? tmp[lane] : 0u;
+    return max(exc, __reduce_max_sync(0xffffffffu, tv));
 }
 
 // Length of the common prefix of chunk[p ..] (shared memory words d32) and src[q ..] (generic pointer: the
@@ -325,26 +300,27 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     // Thread 0 fetches the descriptor of the NEXT chunk while the current one is parsed, one dependent global load per
     // phase (work counter -> list -> selection -> cut points), so that a chunk starts without that chain of round trips;
     // as soon as the next chunk's bytes are known every thread prefetches a share of them into L2.
-    uint32_t nx_job = 0, nx_k = 0, nx_blk = 0;
-    uint64_t nx_j = 0, nx_cs = 0, nx_len = 0;
     auto next_job = [&](int step) {   // thread 0 only
-        if (step == 0) nx_job = a.job0 + atomicAdd(a.counter, 1u);
-        if (nx_job >= a.job1) return;
+        if (step == 0) sm->nx_job = a.job0 + atomicAdd(a.counter, 1u);
+        const uint32_t nj = sm->nx_job;
+        if (nj >= a.job1) return;
         if (step == 1) {
-            nx_k = a.list[nx_job];
-            nx_blk = a.blk ? a.blk[nx_job] : 0u;
+            sm->nx_k = a.list[nj];
+            sm->nx_blk = a.blk ? a.blk[nj] : 0u;
         } else if (step == 2) {
-            nx_j = a.select ? a.select[nx_k] : (uint64_t)nx_k;
+            sm->nx_j = a.select ? a.select[sm->nx_k] : (uint64_t)sm->nx_k;
         } else if (step == 3) {
-            nx_cs = nx_j ? a.cuts[nx_j - 1] : a.start0;
-            nx_len = a.cuts[nx_j] - nx_cs;
+            const uint64_t j = sm->nx_j;
+            const uint64_t c0 = j ? a.cuts[j - 1] : a.start0;
+            sm->nx_cs = c0;
+            sm->nx_len = a.cuts[j] - c0;
         }
     };
     auto publish_job = [&]() {        // thread 0 only, after the last reader of the current descriptor
-        sm->job = nx_job;
-        sm->blkno = nx_blk;
-        sm->cs = nx_cs;
-        sm->len = nx_len;
+        sm->job = sm->nx_job;
+        sm->blkno = sm->nx_blk;
+        sm->cs = sm->nx_cs;
+        sm->len = sm->nx_len;
     };
     if (t == 0) {
         for (int st = 0; st < 4; st++) next_job(st);
@@ -450,7 +426,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 sm->warp_tmp[16 + warp] = wb;   // < 32 x 65521
             }
             __syncthreads();                    // (also orders the staging before its readers)
-            if (warp == 0) {
+            if (warp == 0) {   // thread 0 is the only reader of the two sums (at the end of the chunk): no barrier after this
                 const uint32_t tot_a = __reduce_add_sync(0xffffffffu, lane < nwarps ? sm->warp_tmp[lane] : 0u);
                 const uint32_t tot_b = __reduce_add_sync(0xffffffffu, lane < nwarps ? sm->warp_tmp[16 + lane] : 0u);
                 if (lane == 0) {
@@ -459,7 +435,6 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 }
             }
         }
-        __syncthreads();
         PROF(0)
         if (t == 0 && a.level != 0) next_job(0);
         const uint32_t nh = n >= 4 ? n - 3 : 0;  // hashed positions
@@ -509,23 +484,12 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 }
                 if (lane == 31) sm->warp_tmp[warp] = inc;
                 __syncthreads();
-                if (warp == 0) {
-                    const uint32_t v = lane < nwarps ? sm->warp_tmp[lane] : 0u;
-                    uint32_t wi = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t tt = __shfl_up_sync(0xffffffffu, wi, o);
-                        if (lane >= (unsigned)o) wi += tt;
-                    }
-                    sm->warp_tmp[lane] = wi - v;
-                    if (lane == 31) {
-                        sm->warp_tmp[32] = wi;
-                        s_E[NBUCKET] = (uint16_t)((wi & 0xffffu) + (wi >> 16));   // the entry past the last full word: everything before it
-                    }
-                }
-                __syncthreads();
-                const uint32_t ex = inc - packed + sm->warp_tmp[warp];
-                uint32_t ra = ex & 0xffffu, rb = (ex >> 16) + (sm->warp_tmp[32] & 0xffffu);
+                // every warp folds the totals of the warps before it by itself (packed sums: no carry between the halves)
+                const uint32_t tv = lane < nwarps ? sm->warp_tmp[lane] : 0u;
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, tv);
+                const uint32_t ex = inc - packed + __reduce_add_sync(0xffffffffu, lane < warp ? tv : 0u);
+                if (t == 0) s_E[NBUCKET] = (uint16_t)((tot & 0xffffu) + (tot >> 16));   // the entry past the last full word: everything before it
+                uint32_t ra = ex & 0xffffu, rb = (ex >> 16) + (tot & 0xffffu);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {   // word = E[2k] | E[2k+1] << 16 -> run | (run + E[2k]) << 16
                     const uint32_t ca = wa[q], cb = wb[q];
@@ -612,13 +576,13 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             PROF(4)
             if (t == 0) {   // the next chunk's bytes are known: announce them for the L2 prefetch below
                 next_job(3);
-                uint64_t pc = nx_cs, pl = nx_len;
+                uint64_t pc = sm->nx_cs, pl = sm->nx_len;
                 if (a.blk) {
-                    pc += (uint64_t)nx_blk * LONG_BLOCK;
-                    pl = pl - (uint64_t)nx_blk * LONG_BLOCK < LONG_BLOCK ? pl - (uint64_t)nx_blk * LONG_BLOCK : LONG_BLOCK;
+                    pc += (uint64_t)sm->nx_blk * LONG_BLOCK;
+                    pl = pl - (uint64_t)sm->nx_blk * LONG_BLOCK < LONG_BLOCK ? pl - (uint64_t)sm->nx_blk * LONG_BLOCK : LONG_BLOCK;
                 }
                 sm->pf_cs = pc;
-                sm->pf_len = nx_job < a.job1 ? (uint32_t)pl : 0u;
+                sm->pf_len = sm->nx_job < a.job1 ? (uint32_t)pl : 0u;
             }
             // ---- P4: matches as RUNS.  A pair (position p, source q) whose four bytes agree and whose
             //      preceding bytes differ starts a run: every position p+k inside it has a match of

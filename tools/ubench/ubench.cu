@@ -45,6 +45,9 @@ KERNEL(sts, , sh[(c * 32 + lane + threadIdx.x) & 4095] = x[c]; x[c] += seed)
 KERNEL(atoms, , atomicMax(&sh[(c * 32 + lane + (threadIdx.x & ~31u)) & 4095], x[c]); x[c] += seed)
 KERNEL(vimnmx, , x[c] = max(x[c] ^ seed, (uint32_t)c))
 KERNEL(sel, , x[c] = x[c] > seed ? x[c] - 1 : seed)
+KERNEL(mulhi, , x[c] = __umulhi(x[c], seed) + c)
+KERNEL(rotmul, , { const uint32_t lo = x[c] * 0x02000000u; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(x[c]) : "r"(x[c]), "r"(0x02000000u), "r"(lo)); })
+KERNEL(rotshf, , x[c] = __funnelshift_r(x[c], x[c], 7) ^ seed)
 
 struct T { const char* name; void (*fn)(uint32_t*, long long*, uint32_t); int per_body; };
 
@@ -57,7 +60,7 @@ int main() {
     T tests[] = {{"shf+lop3", k_lop3, 2}, {"iadd3", k_iadd, 1}, {"imad", k_imad, 1}, {"popc+iadd", k_popc, 2}, {"ffs(brev+flo)+iadd", k_ffs, 3},
                  {"brev+iadd", k_brev, 2}, {"prmt", k_prmt, 1}, {"shf", k_shf, 1}, {"isetp+vote+iadd", k_vote, 3}, {"shfl+iadd", k_shfl, 2},
                  {"match.any+lop+iadd", k_match, 3}, {"redux+iadd", k_redux, 2}, {"lds(+3 addr)", k_lds, 4}, {"sts+iadd", k_sts, 2},
-                 {"atoms.max+iadd", k_atoms, 2}, {"lop3+vimnmx", k_vimnmx, 2}, {"isetp+sel(+iadd)", k_sel, 3}};
+                 {"atoms.max+iadd", k_atoms, 2}, {"lop3+vimnmx", k_vimnmx, 2}, {"isetp+sel(+iadd)", k_sel, 3}, {"imad.hi+iadd", k_mulhi, 2}, {"rot = imad + imad.hi", k_rotmul, 2}, {"rot = shf (+lop3)", k_rotshf, 2}};
     for (auto& t : tests) {
         t.fn<<<sms, 1024>>>(out, cyc, 12345u);
         cudaDeviceSynchronize();
