@@ -511,31 +511,46 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             //      position of the same tile there (same tile <=> the two differ only below the tile bits) makes the slot
             //      a candidate for the fix-up below.  The test runs in the shadow of the next tile's atomic; a slot the
             //      chunk has not filled yet holds a stale position, which at worst adds a candidate.
+            //      The loop is a three-stage pipeline, one barrier a trip: a trip ISSUES the atomic of its tile and goes to
+            //      the barrier without touching the result (the barrier orders the atomics of consecutive tiles whether or
+            //      not their values have come back); the next trip stores the position into the slot the atomic returned;
+            //      the trip after that looks at the right-hand neighbour.
             uint16_t* wlist = reinterpret_cast<uint16_t*>(mptr) + warp * (nmax / 16);   // <= 32 candidates per tile and warp
             uint32_t wcnt = 0;   // warp-uniform
             {
                 if (t == 0) s_sorted[nh] = 0xFFFFu;   // no tile holds position 0xFFFF
                 const uint32_t lt = (1u << lane) - 1u;
-                uint32_t chk_slot = 0xffffffffu, chk_p = 0;
-                for (uint32_t p0 = 0; p0 < nh + T; p0 += T) {   // the last trip only looks at the last tile
+                constexpr uint32_t NONE = 0xffffffffu;
+                uint32_t chk_slot = NONE, chk_p = 0;   // stored in the trip before: neighbour not looked at yet
+                uint32_t hn = t < nh ? (uint32_t)s_h16[t] : 0u;   // the hash of the position this trip scatters
+                // cur_*: this trip's atomic (issued here, consumed in the next trip); prv_*: the one issued a trip ago
+                auto trip = [&](uint32_t p0, uint32_t& cur_old, uint32_t& cur_sh, uint32_t& cur_p, uint32_t prv_old, uint32_t prv_sh,
+                                uint32_t prv_p) {
                     const uint32_t p = p0 + t;
-                    uint32_t old = 0, sh = 0;
+                    cur_p = NONE;
                     if (p < nh) {
-                        const uint32_t h1 = (uint32_t)s_h16[p] + 1;
-                        sh = 16 * (h1 & 1);
-                        old = atomicAdd(&s_cnt32[h1 >> 1], 1u << sh);
+                        const uint32_t h1 = hn + 1;
+                        cur_sh = 16 * (h1 & 1);
+                        cur_old = atomicAdd(&s_cnt32[h1 >> 1], 1u << cur_sh);
+                        cur_p = p;
                     }
-                    const bool cand = chk_slot != 0xffffffffu && ((uint32_t)s_sorted[chk_slot + 1] ^ chk_p) < (uint32_t)T_PARSE;
+                    const bool cand = chk_slot != NONE && ((uint32_t)s_sorted[chk_slot + 1] ^ chk_p) < (uint32_t)T_PARSE;
                     const uint32_t b = __ballot_sync(0xffffffffu, cand);
                     if (cand) wlist[wcnt + __popc(b & lt)] = (uint16_t)chk_slot;
                     wcnt += __popc(b);
-                    chk_slot = 0xffffffffu;
-                    if (p < nh) {
-                        chk_slot = (old >> sh) & 0xffffu;
-                        chk_p = p;
-                        s_sorted[chk_slot] = (uint16_t)p;
+                    chk_slot = NONE;
+                    if (prv_p != NONE) {
+                        chk_slot = (prv_old >> prv_sh) & 0xffffu;
+                        chk_p = prv_p;
+                        s_sorted[chk_slot] = (uint16_t)prv_p;
                     }
+                    if (p + T < nh) hn = s_h16[p + T];
                     __syncthreads();
+                };
+                uint32_t oa = 0, sa = 0, pa = NONE, ob = 0, sb = 0, pb = NONE;
+                for (uint32_t p0 = 0; p0 < nh + 2 * T; p0 += 2 * T) {   // the last two trips only drain the pipeline
+                    trip(p0, oa, sa, pa, ob, sb, pb);
+                    trip(p0 + T, ob, sb, pb, oa, sa, pa);
                 }
             }
             PROF(3)
