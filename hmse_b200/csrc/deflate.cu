@@ -994,6 +994,7 @@ __device__ void warp_tree_lengths(HuffWork& hw, uint32_t k, int maxbits, uint8_t
     }
     __syncwarp();
     const uint32_t root = 2 * k - 2;
+    unsigned long long kr = 0;   // the Kraft sum: per-lane partial sums, one reduction (a 64-bit shared atomic is a CAS loop)
     for (uint32_t i = lane; i < k; i += 32) {
         uint32_t node = i, dpt = 0;
         while (node != root) {
@@ -1002,8 +1003,11 @@ __device__ void warp_tree_lengths(HuffWork& hw, uint32_t k, int maxbits, uint8_t
         }
         if (dpt > (uint32_t)maxbits) dpt = (uint32_t)maxbits;
         atomicAdd(&bl32[dpt], 1u);
-        atomicAdd(kraft, 1ull << (maxbits - dpt));
+        kr += 1ull << (maxbits - dpt);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) kr += __shfl_xor_sync(0xffffffffu, kr, o);
+    if (lane == 0) *kraft = kr;
     __syncwarp();
     if (lane == 0) {
         for (int b = 0; b < 16; b++) hw.bl_count[b] = (uint16_t)bl32[b];
