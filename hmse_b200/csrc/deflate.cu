@@ -139,6 +139,7 @@ __host__ __device__ constexpr uint32_t cnt_words(int own) {   // words of the bu
     return (own_cap(own) + dict_cap(own)) * (T_PARSE / 32) > CNT_WORDS ? (own_cap(own) + dict_cap(own)) * (T_PARSE / 32) : CNT_WORDS;
 }
 constexpr uint32_t PAD_FRONT = 16;   // bytes before the chunk in shared memory: the last one is the "byte before position 0"
+constexpr uint32_t BIG_GROUP = 16;   // P3b: same-tile groups up to this size are sorted by the thread of their first slot
 constexpr uint32_t PAD_SORTED = 16;  // bytes before s_sorted: its last u16 is the sentinel s_sorted[-1]
 
 struct ParseSm {  // fixed-size shared state of parse_kernel
@@ -148,8 +149,8 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t job, blkno;        // the chunk (or block of a long chunk) being parsed: fetched by thread 0 while the
     uint64_t cs, len;           //   previous one was parsed (job >= job1: none left)
     uint64_t pf_cs;             // next chunk, announced early so that all threads can prefetch it into L2
-    uint32_t pf_len, pad0;
-    uint32_t nx_job, nx_k, nx_blk, pad1;   // the descriptor being fetched (thread 0's state: kept here, not in registers
+    uint32_t pf_len, big_n;     // big_n: same-tile groups too long for one thread (P3b), sorted by the whole CTA
+    uint32_t nx_job, nx_k, nx_blk, big_g;   // the descriptor being fetched (thread 0's state: kept here, not in registers
     uint64_t nx_j, nx_cs, nx_len;          //   that every thread would carry through all phases)
     uint32_t adler_a, adler_b;
 };
@@ -295,7 +296,10 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     uint16_t* s_exit = s_sorted;
     // the byte "before position 0" of every chunk (never equal to DICT_PREV0: (0, 0) is always a run head), so that the
     // signature of a position needs no special case for p == 0; never overwritten
-    if (t == 0) reinterpret_cast<uint32_t*>(smem)[PAD_FRONT / 4 - 1] = CHUNK_PREV0 << 24;
+    if (t == 0) {
+        reinterpret_cast<uint32_t*>(smem)[PAD_FRONT / 4 - 1] = CHUNK_PREV0 << 24;
+        sm->big_n = 0;
+    }
 
     // Thread 0 fetches the descriptor of the NEXT chunk while the current one is parsed, one dependent global load per
     // phase (work counter -> list -> selection -> cut points), so that a chunk starts without that chain of round trips;
@@ -569,9 +573,13 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                         if ((l ^ p) < (uint32_t)T_PARSE && s_h16[l] == h) return;       // not the first slot of its group
                     }
                     uint32_t g = 2;
-                    for (;; g++) {                                                        // (the sentinel at nh ends the last group)
+                    for (; g <= BIG_GROUP; g++) {                                         // (the sentinel at nh ends the last group)
                         const uint32_t q = s_sorted[i + g];
                         if ((q ^ p) >= (uint32_t)T_PARSE || s_h16[q] != h) break;
+                    }
+                    if (g > BIG_GROUP) {   // repetitive data (a run of one byte fills a tile with ONE group): left to the whole CTA
+                        s_cnt32[atomicAdd(&sm->big_n, 1u)] = i;
+                        return;
                     }
                     for (uint32_t x = 1; x < g; x++) {                                    // insertion sort of g (mostly 2) positions
                         const uint32_t v = s_sorted[i + x];
@@ -588,6 +596,32 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 for (uint32_t j = lane; j < wcnt; j += 32) sort_group(wlist[j]);
             }
             __syncthreads();
+            if (const uint32_t nbig = sm->big_n) {   // CTA-uniform; never taken on text
+                // A long group (up to a whole tile) by all threads: its extent by one test per slot and a minimum, then a
+                // rank sort - thread x counts the members smaller than its own (all positions differ) and moves it there.
+                // One thread would need a quadratic number of dependent steps: milliseconds per chunk on constant data.
+                for (uint32_t bg = 0; bg < nbig; bg++) {
+                    const uint32_t i0 = s_cnt32[bg];
+                    const uint32_t p = s_sorted[i0], h = s_h16[p];
+                    if (t == 0) sm->big_g = T;
+                    __syncthreads();
+                    {
+                        const uint32_t q = i0 + t <= nh ? (uint32_t)s_sorted[i0 + t] : 0xFFFFu;
+                        if ((q ^ p) >= (uint32_t)T_PARSE || s_h16[q & 0x7fffu] != h) atomicMin(&sm->big_g, t);
+                    }
+                    __syncthreads();
+                    const uint32_t g = sm->big_g;
+                    uint32_t v = 0, rank = 0;
+                    if (t < g) {
+                        v = s_sorted[i0 + t];
+                        for (uint32_t j = 0; j < g; j++) rank += (uint32_t)s_sorted[i0 + j] < v;
+                    }
+                    __syncthreads();
+                    if (t < g) s_sorted[i0 + rank] = (uint16_t)v;
+                }
+                __syncthreads();
+                if (t == 0) sm->big_n = 0;
+            }
             PROF(4)
             if (t == 0) {   // the next chunk's bytes are known: announce them for the L2 prefetch below
                 next_job(3);

@@ -209,3 +209,65 @@ def test_shifted_text_like_data(ctx, corpus8):
         cuts = oracle.chunk_c(d)
         blob, offs = hmse_b200.compress(d, cuts, None, zd, ctx=ctx)
         _roundtrip(d, cuts, None, zd, blob, offs)
+
+
+def test_stream_sizes_equal_the_cpu_model(ctx, corpus8):
+    """The kernel's candidate sets (nearest 2 / 3 / 4 own positions of the 13-bit bucket by size class, nearest 4 of the
+    15-bit dictionary bucket, run heads only), its lazy parse and its Huffman codes are restated sequentially in
+    tests/model/deflate_model.cpp: per-chunk stream sizes must agree EXACTLY on text.  This pins what the parallel sort,
+    the run screen, the prefix max and the chain passes compute, beyond "it inflates and is small enough"."""
+    import ctypes as C
+
+    import hmse_b200
+    from tests.model.build import Params, build
+
+    lib = build()
+    data = corpus8[:3 << 20]
+    zd = corpus.zdict()
+    cuts = oracle.chunk_c(data)
+    blob, offs = hmse_b200.compress(data, cuts, None, zd, ctx=ctx)
+    sizes = np.diff(np.asarray(offs).astype(np.int64))
+    zdn = np.frombuffer(zd, dtype=np.uint8)
+    out = np.zeros(70000, dtype=np.uint8)
+    prs = {own: Params(hash_bytes=4, chain_own=own, chain_dict=4, lazy=1, too_far=0, dict_hash_bits=15, mode=2, min_len=0)
+           for own in (2, 3, 4)}
+    starts = np.concatenate([[0], cuts[:-1]]).astype(np.int64)
+    bad = []
+    for k, (s, e) in enumerate(zip(starts.tolist(), cuts.astype(np.int64).tolist())):
+        ch = np.ascontiguousarray(data[s:e])
+        pr = prs[2 if e - s <= 13312 else 3 if e - s <= 20480 else 4]
+        r = lib.model_compress(ch.ctypes.data, e - s, zdn.ctypes.data, len(zd), C.byref(pr), out.ctypes.data, out.size, None)
+        if r != sizes[k]:
+            bad.append((k, e - s, int(sizes[k]), int(r)))
+    assert not bad, "GPU stream sizes differ from the CPU model: %s" % bad[:5]
+
+
+def test_repetitive_data_is_not_pathologically_slow(ctx, corpus8):
+    """A run of one byte puts every position of a 512-byte tile into ONE hash bucket: the bucket sort of parse_kernel
+    must not fall back to a quadratic walk by a single thread there (it once did: 0.11 GB/s on zeros against 32 on text).
+    Relative bound, generous: zeros and a 7-byte period compress at no less than 1/20 of the text rate."""
+    import torch
+
+    n = 8 << 20
+    zd = ctx.stage(corpus.zdict())
+    cuts = ctx.stage_u64(np.arange(8192, n + 1, 8192, dtype=np.uint64))
+
+    def rate(data):
+        d = ctx.stage(data)
+        ctx.compress(d, cuts, None, zd)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        blob, offs = ctx.compress(d, cuts, None, zd)
+        b.record()
+        torch.cuda.synchronize()
+        return n / a.elapsed_time(b), blob, offs
+
+    text_rate, _, _ = rate(corpus8[:n])
+    for name, data in (("zeros", np.zeros(n, dtype=np.uint8)),
+                       ("period7", np.frombuffer((b"abcdefg" * (n // 7 + 1))[:n], dtype=np.uint8))):
+        r, blob, offs = rate(data)
+        assert r >= text_rate / 20, "%s: %.2f of the text rate" % (name, r / text_rate)
+        hb, ho = blob.cpu().numpy(), offs.cpu().numpy().view(np.uint64)
+        for k in (0, 1, cuts.numel() - 1):
+            raw = zlib.decompressobj(zdict=corpus.zdict()).decompress(hb[int(ho[k]):int(ho[k + 1])].tobytes())
+            assert raw == data[k * 8192:(k + 1) * 8192].tobytes()
