@@ -6,14 +6,16 @@
 // and the zlib level-6 lazy rule becomes a pure function next(p), so the parse is chain
 // following.  Three kernels per batch of chunks, so that no phase leaves a CTA idle:
 //
-//  parse_kernel    one CTA per chunk (persistent, two size classes).
-//     P0 stage chunk in shared memory + Adler-32      P4 match search, one thread per SORTED index
-//     P1 histogram of 4-byte hashes (13 bits)            (lanes of a warp share a bucket: similar
-//     P2 scan -> bucket starts                            chain lengths, broadcast loads), own
-//     P3 tile-ordered scatter + bucket fix-up sort        buckets in shared memory, dictionary
-//        (positions ascending: nearest-first search,      buckets (host-built index) from L1/L2
-//        deterministic output)                         P5 per-32-byte-range backward DP of chain exits
-//                                                      P6 hop the true chain across ranges
+//  parse_kernel    one CTA per chunk (persistent, three size classes; the next chunk's descriptor and bytes are fetched
+//                  while the current one is parsed).
+//     P0 stage chunk in shared memory + Adler-32      P4 match search as RUNS, one lane per SORTED index: a
+//     P1 histogram of 4-byte hashes (13 bits)            screen (own candidates = preceding lanes, dictionary
+//     P2 scan -> bucket starts                            candidates = one 16-byte bucket record), pairs
+//     P3 tile-ordered scatter; positions of one           compacted by ballots into two per-warp lists and
+//        bucket that fell into one tile are put in        extended 32 at a time
+//        order by the thread of their first slot      P4c prefix max of run ends -> match words
+//        (positions ascending: nearest-first search,  P5 per-32-byte-range backward DP of chain exits
+//        deterministic output)                         P6 hop the true chain across ranges
 //                                                      P7 symbol histograms + compact u16 token stream
 //  huffman_kernel  one WARP per chunk: length-limited Huffman lengths (two-queue merge by lane 0,
 //                  everything else lane-parallel), canonical codes, dynamic header, block type
@@ -140,7 +142,7 @@ __host__ __device__ constexpr uint32_t cnt_words(int own) {   // words of the bu
 }
 constexpr uint32_t PAD_FRONT = 16;   // bytes before the chunk in shared memory: the last one is the "byte before position 0"
 constexpr uint32_t BIG_GROUP = 16;   // P3b: same-tile groups up to this size are sorted by the thread of their first slot
-constexpr uint32_t PAD_SORTED = 16;  // bytes before s_sorted: its last u16 is the sentinel s_sorted[-1]
+constexpr uint32_t PAD_SORTED = 16;  // bytes between the chunk's slack and s_sorted (keeps the 16-byte alignment of what follows)
 
 struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t hist[REC_WORDS];
@@ -692,11 +694,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     if (lane < count) {
                         const uint32_t rec = lds_w(first + 4u * lane);
                         const uint32_t p = rec & 0x7fffu, q = rec >> 17;
-#ifdef EXP_CAP_LIM
-                        const uint32_t lim = min(n - p, (uint32_t)EXP_CAP_LIM);
-#else
                         const uint32_t lim = n - p;
-#endif
                         const uint32_t sa = p * 8u, sb = q * 8u;   // funnel shifts take the amount modulo 32
                         const uint32_t* A = s_data32 + (p >> 2);
                         const uint32_t* B = s_data32 + (q >> 2);
@@ -726,11 +724,7 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                     if (lane < count) {
                         const uint32_t rec = lds_w(first + 4u * lane);
                         const uint32_t p = rec & 0x7fffu, q = rec >> 17;
-#ifdef EXP_CAP_LIM
-                        const uint32_t lim = min(min(n - p, dlen - q), (uint32_t)EXP_CAP_LIM);
-#else
                         const uint32_t lim = min(n - p, dlen - q);   // matches do not run from the dictionary into the chunk
-#endif
                         const uint32_t sa = p * 8u, sb = q * 8u;
                         const uint32_t* A = s_data32 + (p >> 2);
                         const uint32_t* B = dictw + (q >> 2);
