@@ -219,7 +219,9 @@ uint64_t hmse_compress_bound(uint64_t len);
  * level 6) or 0 (stored blocks); anything else fails with HMSE_E_INVAL.  *total (host) = d_offsets[m].
  * d_out == NULL with out_cap == 0: everything but the final copy is done (sizes only, HMSE_OK).  On HMSE_E_CAPACITY
  * *total holds the required out_cap.  In both cases the streams stay staged inside ctx until the next hmse_compress and
- * hmse_compress_pack copies them out - the chunks are never compressed twice. */
+ * hmse_compress_pack copies them out - the chunks are never compressed twice.
+ * d_data: 4-byte aligned, and 16 readable bytes must follow the last chunk (chunks are staged with aligned 16-byte
+ * vector loads: the vector that holds a chunk's last byte is read whole). */
 int hmse_compress(hmse_ctx* ctx, const uint8_t* d_data, uint64_t start0, const uint64_t* d_cuts,
                   const uint64_t* d_select, uint64_t m, const uint8_t* d_zdict, uint32_t dict_len,
                   int level, uint8_t* d_out, uint64_t out_cap, uint64_t* d_offsets, uint64_t* total,
