@@ -155,6 +155,7 @@ struct ParseSm {  // fixed-size shared state of parse_kernel
     uint32_t nx_job, nx_k, nx_blk, big_g;   // the descriptor being fetched (thread 0's state: kept here, not in registers
     uint64_t nx_j, nx_cs, nx_len;          //   that every thread would carry through all phases)
     uint32_t adler_a, adler_b;
+    uint8_t lsym[256];          // length symbol - 257 of match length 3 + i (P7 looks it up instead of computing it)
 };
 
 // Dictionary bucket of a 4-byte value; the own-chunk bucket hash4(v) is its top HASH_BITS bits.
@@ -301,6 +302,11 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
     if (t == 0) {
         reinterpret_cast<uint32_t*>(smem)[PAD_FRONT / 4 - 1] = CHUNK_PREV0 << 24;
         sm->big_n = 0;
+    }
+    for (uint32_t i = t; i < 256; i += T) {
+        uint32_t sy, eb, ev;
+        len_sym(i + 3, sy, eb, ev);
+        sm->lsym[i] = (uint8_t)(sy - 257);
     }
 
     // Thread 0 fetches the descriptor of the NEXT chunk while the current one is parsed, one dependent global load per
@@ -918,7 +924,10 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
             }
             __syncthreads();
             PROF(7)
-            // ---- P7: symbol histograms + token words (literal: byte; match: 0x8000|len, dist-1) ----
+            // ---- P7: symbol histograms + token words (literal: byte; match: 0x8000|len, dist-1).  A thread walks the
+            //      tokens of its ranges twice (count, then write); lanes hold literals and matches at the same time, so a
+            //      step is written without a branch on the token kind: the first symbol is the byte or a looked-up length
+            //      symbol, the distance symbol comes from a logarithm and is counted under a predicate. ----
             uint32_t words = 0;
             for (uint32_t r = r0; r < r1; r++) {
                 const uint32_t e = s_entry[r];
@@ -926,19 +935,15 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 const uint32_t pe = ((r << RS) + RL < n) ? (r << RS) + RL : n;
                 for (uint32_t p = (r << RS) + e; p < pe;) {
                     const uint32_t mw = mptr[SK(p)];
-                    if (mw_is_match(mw)) {
-                        uint32_t sy, eb, ev;
-                        len_sym(mw >> 16, sy, eb, ev);
-                        atomicAdd(&sm->hist[sy], 1u);
-                        dist_sym((mw & 0x7fffu) + 1, sy, eb, ev);
-                        atomicAdd(&sm->hist[288 + sy], 1u);
-                        words += 2;
-                        p += mw >> 16;
-                    } else {
-                        atomicAdd(&sm->hist[s_data[p]], 1u);
-                        words += 1;
-                        p += 1;
-                    }
+                    const bool m = mw_is_match(mw);
+                    const uint32_t L = mw >> 16, d = mw & 0x7fffu;   // d = distance - 1
+                    const uint32_t s1 = m ? 257u + sm->lsym[m ? L - 3 : 0u] : (uint32_t)s_data[p];
+                    atomicAdd(&sm->hist[s1], 1u);
+                    const uint32_t eb = (uint32_t)(31 - __clz((int)(d | 2u))) - 1u;   // 0 for d < 4
+                    const uint32_t sy = d < 4 ? d : 2 * eb + 2 + ((d >> eb) & 1u);
+                    if (m) atomicAdd(&sm->hist[288 + sy], 1u);
+                    words += m ? 2u : 1u;
+                    p += m ? L : 1u;
                 }
             }
             uint32_t w_off = block_excl_scan(words, sm->warp_tmp, &n_words);
@@ -951,14 +956,12 @@ __global__ void __launch_bounds__(T_PARSE, 2) parse_kernel(DeflArgs a) {
                 const uint32_t pe = ((r << RS) + RL < n) ? (r << RS) + RL : n;
                 for (uint32_t p = (r << RS) + e; p < pe;) {
                     const uint32_t mw = mptr[SK(p)];
-                    if (mw_is_match(mw)) {
-                        s_tok[w_off++] = (uint16_t)(0x8000u | (mw >> 16));
-                        s_tok[w_off++] = (uint16_t)(mw & 0x7fffu);
-                        p += mw >> 16;
-                    } else {
-                        s_tok[w_off++] = s_data[p];
-                        p += 1;
-                    }
+                    const bool m = mw_is_match(mw);
+                    const uint32_t L = mw >> 16;
+                    s_tok[w_off] = m ? (uint16_t)(0x8000u | L) : (uint16_t)s_data[p];
+                    if (m) s_tok[w_off + 1] = (uint16_t)(mw & 0x7fffu);
+                    w_off += m ? 2u : 1u;
+                    p += m ? L : 1u;
                 }
             }
             __syncthreads();
