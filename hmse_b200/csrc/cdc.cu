@@ -4,9 +4,11 @@
 //
 // K1 gear_scan     reads the stream ONCE.  Tiles of 32 KiB are staged into shared memory with
 //                  per-thread 128-byte bulk-async (TMA) copies into bank-conflict-free padded
-//                  slots, double buffered on mbarriers.  A 64-bit Gear hash depends only on
+//                  slots, completion counted on an mbarrier (one buffer per CTA, three CTAs per SM
+//                  cover each other's copies).  A 64-bit Gear hash depends only on
 //                  the trailing 64 bytes, so every thread rolls its own 128-byte run after a
-//                  64-byte warm-up and emits one MaskS bit and one MaskL bit per byte.
+//                  64-byte warm-up and emits one MaskS bit and one MaskL bit per byte; the Gear
+//                  table is replicated sixteen times so that the lookups are bank-conflict free.
 // K2 resolve       sequential FastCDC resets fp at start+min, so next_cut(s) is a pure
 //                  function of s: partial-window positions (64 bytes after the skip) are
 //                  recomputed with a warp scan, the rest is a find-first-set over the
@@ -36,7 +38,9 @@ constexpr int K1_TILE = K1_THREADS * K1_RUN;    // 32 KiB
 constexpr int K1_SLOT = K1_RUN + 16;            // padded slot stride: LDS.128 conflict-free
 constexpr int K1_STAGE = (K1_THREADS + 1) * K1_SLOT;  // slot 0 carries the 64-byte halo
 // REP > 1 keeps REP copies of the Gear table, one per bank pair (row e = the copies of entry e, lane l reads copy l & 15), so
-// that the data-dependent 8-byte lookups of a half-warp never share a bank.  Measured (see hmse_chunk_scan): no gain.
+// that the data-dependent 8-byte lookups of a half-warp never share a bank: with ONE table sixteen random entries fall
+// into sixteen bank pairs about three deep, and at five to six shared-memory wavefronts per byte and warp the lookups,
+// not the arithmetic, bounded the kernel (measured: see hmse_chunk_scan).
 template <int STAGES, int REP>
 struct K1Cfg {
     static constexpr int CTAS = (STAGES == 1 || REP == 1) ? 3 : 2;   // resident CTAs per SM (shared memory bounds it)
@@ -73,31 +77,46 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-#define GEAR_STEP(BYTE, BITPOS)                                      \
-    {                                                                \
-        fp = (fp << 1) + sg[(BYTE) * REP];                           \
-        if ((fp & mc) == 0) {                                        \
-            if ((fp & ms) == 0) sb |= 1ull << (BITPOS);              \
-            if ((fp & ml) == 0) lb |= 1ull << (BITPOS);              \
-        }                                                            \
+// Gear[byte K of W] for this lane.  REP == 1: one table.  REP == 16: lane l reads copy l & 15, entry e of copy c at
+// word 16 e + c, so the 16 lanes of a half-warp hit 16 different bank pairs whatever bytes they hold; the byte is
+// pulled out by one PRMT and scaled and added to the lane's base by one IMAD (the fma pipe is idle in this kernel).
+template <int REP, int K>
+__device__ __forceinline__ uint64_t gear_at(const uint64_t* sg, uint32_t sgl, uint32_t stride, uint32_t W) {
+    if constexpr (REP == 1) {
+        return sg[K == 3 ? (W >> 24) : ((W >> (8 * K)) & 0xffu)];
+    } else {
+        uint32_t lo, hi;
+        const uint32_t a = __byte_perm(W, 0, 0x4440 + K) * stride + sgl;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+        return ((uint64_t)hi << 32) | lo;
+    }
+}
+
+#define GEAR_HIT(FP, BITPOS)                                         \
+    if (((FP) & mc) == 0) {                                          \
+        if (((FP) & ms) == 0) sb |= 1ull << (BITPOS);                \
+        if (((FP) & ml) == 0) lb |= 1ull << (BITPOS);                \
     }
 
-#define GEAR_WORD(W, B0)                       \
-    GEAR_STEP((W) & 0xffu, (B0))               \
-    GEAR_STEP(((W) >> 8) & 0xffu, (B0) + 1)    \
-    GEAR_STEP(((W) >> 16) & 0xffu, (B0) + 2)   \
-    GEAR_STEP((W) >> 24, (B0) + 3)
+#define GEAR_WORD(W, B0)                                             \
+    {                                                                \
+        const uint64_t f0 = (fp << 1) + gear_at<REP, 0>(sg, sgl, stride, (W));   \
+        const uint64_t f1 = (f0 << 1) + gear_at<REP, 1>(sg, sgl, stride, (W));   \
+        const uint64_t f2 = (f1 << 1) + gear_at<REP, 2>(sg, sgl, stride, (W));   \
+        fp = (f2 << 1) + gear_at<REP, 3>(sg, sgl, stride, (W));      \
+        GEAR_HIT(f0, (B0)) GEAR_HIT(f1, (B0) + 1) GEAR_HIT(f2, (B0) + 2) GEAR_HIT(fp, (B0) + 3) \
+    }
 
-#define WARM_WORD(W)                                    \
-    fp = (fp << 1) + sg[((W) & 0xffu) * REP];           \
-    fp = (fp << 1) + sg[(((W) >> 8) & 0xffu) * REP];    \
-    fp = (fp << 1) + sg[(((W) >> 16) & 0xffu) * REP];   \
-    fp = (fp << 1) + sg[((W) >> 24) * REP];
+#define WARM_WORD(W)                                                 \
+    fp = (fp << 1) + gear_at<REP, 0>(sg, sgl, stride, (W));          \
+    fp = (fp << 1) + gear_at<REP, 1>(sg, sgl, stride, (W));          \
+    fp = (fp << 1) + gear_at<REP, 2>(sg, sgl, stride, (W));          \
+    fp = (fp << 1) + gear_at<REP, 3>(sg, sgl, stride, (W));
 
 template <int STAGES, int REP>
 __global__ void __launch_bounds__(K1_THREADS, (K1Cfg<STAGES, REP>::CTAS))
 gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles, const CdcDev* __restrict__ cfg,
-                 uint64_t* __restrict__ bitS, uint64_t* __restrict__ bitL) {
+                 uint64_t* __restrict__ bitS, uint64_t* __restrict__ bitL, uint32_t stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stage0 = smem;
     uint64_t* sg_all = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * K1_STAGE);
@@ -111,6 +130,7 @@ gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles,
     }
     // sg[b * REP] = this lane's copy of entry b (its own bank pair when REP == 16)
     const uint64_t* sg = sg_all + (REP > 1 ? (t & (REP - 1)) : 0);
+    const uint32_t sgl = smem_u32(sg);   // (stride = 8 * REP bytes between entries: a kernel argument, so that it stays an IMAD)
     const uint64_t ms = cfg->ms, ml = cfg->ml, mc = cfg->mc;
     if (t == 0) {
         for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], K1_THREADS);
@@ -455,17 +475,17 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
     const uint64_t words = (n_tiles ? n_tiles : 1) * (K1_TILE / 64);
     HMSE_SCRATCH(ctx, bits, uint64_t*, SLOT_CDC_BITS, 2 * words * sizeof(uint64_t));
     if (n_tiles) {
-        // variant 0 (default): one copy of the Gear table, two staging buffers, 3 CTAs per SM.  HMSE_SCAN_VARIANT selects the
-        // two measured alternatives (tools/scan_variants.py, profiles/r02f_scan_variants.txt): 1 = table replicated 16 times
-        // (one copy per bank pair, lookups conflict free), one staging buffer, 3 CTAs; 2 = replicated, two buffers, 2 CTAs.
-        // Measured on B200 over 10 GB: 8.14 / 8.70 / 9.03 ms - the replicated table is NOT faster, so bank conflicts of the
-        // lookup do not bound this kernel (the serial fp chain and the issue rate do); the variants stay for the record.
-        static int variant = -1;
-        if (variant < 0) {
-            const char* e = getenv("HMSE_SCAN_VARIANT");
-            variant = e ? atoi(e) : 0;
-            if (variant < 0 || variant > 2) variant = 0;
-        }
+        // variant 1 (default): the Gear table replicated 16 times (one copy per bank pair: the lookups of a half-warp never
+        // share a bank), one staging buffer, 3 CTAs per SM.  HMSE_SCAN_VARIANT (read at every call) selects the measured
+        // alternatives (tools/scan_variants.py): 0 = one copy of the table, two staging buffers, 3 CTAs (the default until
+        // the replicated lookup cost no extra instructions); 2 = replicated, two buffers, 2 CTAs.  B200, 4 GB of text
+        // (profiles/r02P_scan_variants.txt): 1410 / 1212 / 1233 GB/s.  Testing four positions per branch was measured
+        // there too and is slower in every combination (1310 / 1214 / 1279 GB/s: it trades branches for ALU-pipe work), and
+        // so is the hash update on the fma pipe (mad.wide + mad: 1269 GB/s, profiles/r02Q_*: ptxas splits the 64-bit
+        // addend off again, twelve instructions per byte instead of ten).
+        const char* ve = getenv("HMSE_SCAN_VARIANT");
+        int variant = ve ? atoi(ve) : 1;
+        if (variant < 0 || variant > 2) variant = 1;
         const CdcDev* dc = (const CdcDev*)ctx->slot[SLOT_CDC_CFG];
         HT_BEGIN(ctx, HT_SCAN, st);
         KL(ctx);
@@ -476,7 +496,7 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
         const uint64_t resident = (uint64_t)ctx->sm_count * K1Cfg<ST, RP>::CTAS;                                              \
         const uint64_t grid = n_tiles < resident ? n_tiles : resident;                                                        \
         gear_scan_kernel<ST, RP><<<(unsigned)grid, K1_THREADS, K1Cfg<ST, RP>::SMEM, st>>>(d_data, n_avail, n_tiles, dc, bits, \
-                                                                                          bits + words);                      \
+                                                                                          bits + words, 8u * RP);                      \
     }
         if (variant == 0) K1_LAUNCH(2, 1)
         else if (variant == 2) K1_LAUNCH(2, 16)

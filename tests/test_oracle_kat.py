@@ -57,6 +57,32 @@ def test_minhash_matches_murmur_definition():
     assert (short == 0xFFFFFFFF).all()
 
 
+def test_murmur3_and_minhash_against_an_independent_implementation():
+    """MurmurHash3_x86_32 is a third-party primitive the spec names (murmur3.h, README.md:2573, 2591) and does not
+    vendor.  scikit-learn ships its own C++ copy of Appleby's function (sklearn.utils.murmurhash3_32, written by other
+    people): the oracle's hash (random keys of every length 0..40, random seeds) and whole MinHash signatures - NumPy
+    and C restatements - must equal what that implementation gives, so the pin does not rest on twelve vectors alone."""
+    sk = pytest.importorskip("sklearn.utils")
+    rng = np.random.default_rng(2024)
+    for n in range(0, 41):
+        for _ in range(8):
+            key = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            seed = int(rng.integers(0, 1 << 32))
+            assert oracle.murmur3_32(key, seed) == sk.murmurhash3_32(key, seed=seed, positive=True)
+    data = corpus.generate(6000)
+    cuts = np.array([1000, 1003, 4096, 6000], dtype=np.uint64)      # a 3-byte chunk among them
+    sig = oracle.minhash(data, cuts)
+    assert np.array_equal(sig, oracle.minhash_c(data, cuts))
+    raw = data.tobytes()
+    lo = 0
+    for j, hi in enumerate(int(c) for c in cuts):
+        shingles = {raw[i:i + 4] for i in range(lo, hi - 3)}
+        for p in (0, 17, 127):
+            want = min((sk.murmurhash3_32(s, seed=p + 1, positive=True) for s in shingles), default=0xFFFFFFFF)
+            assert int(sig[j, p]) == want
+        lo = hi
+
+
 def test_zlib_preset_dictionary_framing():
     zd = corpus.zdict()
     data = corpus.generate(20000)
