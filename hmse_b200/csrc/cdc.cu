@@ -17,6 +17,7 @@
 //                  the chain merges with the speculative one (chains converge in a few
 //                  chunks); rounds repeat until no segment exit changes.  The same mechanism
 //                  stitches byte-range shards across GPUs (hmse_chunk_resolve with `entry`).
+#include <cuda.h>   // CUtensorMap types only: the encoder is looked up at run time (cudaGetDriverEntryPoint), no -lcuda
 #include <stdlib.h>
 
 #include "ctx.cuh"
@@ -218,6 +219,229 @@ gear_scan_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t n_tiles,
         ol[0] = make_uint4((uint32_t)lw[0], (uint32_t)(lw[0] >> 32), (uint32_t)lw[1], (uint32_t)(lw[1] >> 32));
         __syncthreads();  // everyone is done reading stage s before it is refilled
     }
+}
+
+// The same scan with runs that CONTINUE across tiles (HMSE_SCAN_VARIANT=3 / 4, experimental): a thread owns `tpt`
+// consecutive 128-byte runs of the stream (a region of 256 * tpt * 128 bytes per CTA trip) and carries its hash from one
+// to the next, so the 64-byte warm-up is paid once per tpt runs instead of once per run (a third of all hashing
+// otherwise).  A thread reads only its own bytes, so the slots of a warp are nobody else's business: no __syncthreads in
+// the loop.  The warm-up bytes come straight from global memory (four 16-byte loads per region and thread).  Bitmaps
+// and cut lists are the same bit for bit: the hash at a position is the sum of the trailing 64 bytes' table entries
+// whatever came before.
+// Staging.  BULK: one 128-byte bulk-async (TMA) copy per thread and tile, counted on the CTA's mbarrier - ptxas
+//   serialises the 32 copies of a warp (UBLKCP takes uniform registers: an ELECT / R2UR / UBLKCP loop of ~8
+//   instructions per lane, a sixth of the kernel's instructions).  !BULK: 16-byte cp.async (LDGSTS) copies - the eight
+//   lanes of a group fetch ONE lane's 128-byte line per instruction (whole sectors, a conflict-free 128-byte write),
+//   eight instructions a tile; completion per warp (wait_group + __syncwarp), and every lane prefetches its next line
+//   into L2 while the current one is hashed.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(K1_THREADS, 3)
+gear_scan_cont_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t byte0, uint64_t n_regions, uint32_t tpt, uint64_t words,
+                      const CdcDev* __restrict__ cfg, uint64_t* __restrict__ bitS, uint64_t* __restrict__ bitL, uint32_t stride) {
+    constexpr int REP = 16;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stage0 = smem;
+    uint64_t* sg_all = reinterpret_cast<uint64_t*>(smem + (size_t)K1_STAGE);
+    uint64_t* bars = sg_all + REP * 256;
+    const unsigned t = threadIdx.x, lane = t & 31;
+    {
+        const uint64_t g = cfg->gear[t];
+#pragma unroll
+        for (int c = 0; c < REP; c++) sg_all[t * REP + c] = g;
+    }
+    const uint64_t* sg = sg_all + (t & (REP - 1));
+    const uint32_t sgl = smem_u32(sg);
+    const uint64_t ms = cfg->ms, ml = cfg->ml, mc = cfg->mc;
+    if (BULK && t == 0) {
+        mbar_init(&bars[0], K1_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t n_pad = (n + 15) & ~15ull;
+    const uint64_t span = (uint64_t)tpt * K1_RUN;   // bytes of one thread per region
+    uint8_t* slot = stage0 + (size_t)(t + 1) * K1_SLOT;
+    uint32_t it = 0;
+    for (uint64_t region = blockIdx.x; region < n_regions; region += gridDim.x) {
+        const uint64_t region_base = byte0 + region * (span * K1_THREADS);   // (byte0: the kernel may cover a tail of the stream only)
+        const uint64_t my_base = region_base + (uint64_t)t * span;
+        uint64_t fp = 0;
+        if (my_base >= 64 && my_base < n) {   // the 64 bytes before the first run (my_base is a multiple of 128: aligned)
+            const uint4* wp = reinterpret_cast<const uint4*>(data + my_base - 64);
+            uint4 wv[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) wv[q] = __ldg(wp + q);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 v = wv[q];
+                WARM_WORD(v.x) WARM_WORD(v.y) WARM_WORD(v.z) WARM_WORD(v.w)
+            }
+        }
+        for (uint32_t i = 0; i < tpt; i++, it++) {
+            const uint64_t pos = my_base + (uint64_t)i * K1_RUN;
+            if constexpr (BULK) {
+                uint32_t bytes = 0;
+                if (pos < n_pad) {
+                    const uint64_t left = n_pad - pos;
+                    bytes = left < K1_RUN ? (uint32_t)left : (uint32_t)K1_RUN;
+                }
+                // (a thread that is past its wait of trip `it` has seen every thread arrive for it: nobody is a whole
+                //  phase ahead, and the slot is read by its owner only)
+                mbar_arrive_tx(&bars[0], bytes);
+                if (bytes) bulk_g2s(slot, data + pos, bytes, &bars[0]);
+                mbar_wait(&bars[0], it & 1);
+            } else {
+                // lane l = 8 g + c copies 16-byte chunk c of the line of lane 8 g + k, k = 0 .. 7
+                const uint32_t c16 = (lane & 7u) * 16u;
+                const uint64_t grp_pos = pos - (uint64_t)(lane & 7u) * span + c16;       // chunk c of lane 8 g
+                uint8_t* grp_slot = slot - (size_t)(lane & 7u) * K1_SLOT + c16;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint64_t sp = grp_pos + (uint64_t)k * span;
+                    const bool in = sp < n_pad;   // chunks are 16-byte granular and so is n_pad: all or nothing
+                    cp_async16(grp_slot + (size_t)k * K1_SLOT, data + (in ? sp : 0), in ? 16u : 0u);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (i + 1 < tpt && pos + K1_RUN < n_pad) asm volatile("prefetch.global.L2 [%0];" ::"l"(data + pos + K1_RUN));
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+            uint64_t sw[2] = {0, 0}, lw[2] = {0, 0};
+            if (pos < n) {
+                const uint4* rp = reinterpret_cast<const uint4*>(slot);
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    uint64_t sb = 0, lb = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint4 v = rp[w * 4 + q];
+                        GEAR_WORD(v.x, q * 16)
+                        GEAR_WORD(v.y, q * 16 + 4)
+                        GEAR_WORD(v.z, q * 16 + 8)
+                        GEAR_WORD(v.w, q * 16 + 12)
+                    }
+                    sw[w] = sb;
+                    lw[w] = lb;
+                }
+                const uint64_t left = n - pos;   // positions >= n (stale bytes in the slot) never become candidates
+                if (left < K1_RUN) {
+#pragma unroll
+                    for (int w = 0; w < 2; w++) {
+                        const uint64_t keep = left >= 64ull * (w + 1) ? ~0ull : (left <= 64ull * w ? 0ull : ((1ull << (left - 64 * w)) - 1));
+                        sw[w] &= keep;
+                        lw[w] &= keep;
+                    }
+                }
+            }
+            const uint64_t wbase = pos >> 6;   // even: one 16-byte store per mask (a region may end past the bitmaps)
+            if (wbase < words) {
+                *reinterpret_cast<uint4*>(bitS + wbase) = make_uint4((uint32_t)sw[0], (uint32_t)(sw[0] >> 32), (uint32_t)sw[1], (uint32_t)(sw[1] >> 32));
+                *reinterpret_cast<uint4*>(bitL + wbase) = make_uint4((uint32_t)lw[0], (uint32_t)(lw[0] >> 32), (uint32_t)lw[1], (uint32_t)(lw[1] >> 32));
+            }
+            if constexpr (!BULK) __syncwarp();   // the slots of this warp are refilled by its other lanes
+        }
+    }
+}
+
+// HMSE_SCAN_VARIANT=5 (experimental): the continuing runs staged by ONE tensor-map TMA copy per tile and CTA.  The
+// stream is described to the TMA unit as a 3-D tensor {byte in a thread's span, thread (256), region}; tile i of a
+// region is the box {128 bytes, 256 threads, 1} at {128 i, 0, region}: 256 rows of 128 bytes, one per thread, 32 KB,
+// fetched by a single cp.async.bulk.tensor issued by one thread - no per-thread copies, no staging instructions at all.
+// SWIZZLE_128B lays the box out densely and XORs the 16-byte chunk index with the row index (mod 8), so that the eight
+// lanes of a quarter-warp, which read the same chunk of eight consecutive rows, hit eight different bank groups.
+// Only whole regions go through this kernel; the tail of the stream is scanned by gear_scan_cont_kernel from byte0.
+__global__ void __launch_bounds__(K1_THREADS, 3)
+gear_scan_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ data, uint64_t n_regions, uint32_t tpt,
+                     const CdcDev* __restrict__ cfg, uint64_t* __restrict__ bitS, uint64_t* __restrict__ bitL, uint32_t stride) {
+    constexpr int REP = 16;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // the swizzled box needs a 1024-byte aligned home (the launch asks for 1 KB more than the layout needs)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stage = smem;                                                  // 256 rows x 128 bytes
+    uint64_t* sg_all = reinterpret_cast<uint64_t*>(smem + K1_TILE);         // 32 KB table
+    uint64_t* bar = sg_all + REP * 256;
+    const unsigned t = threadIdx.x;
+    {
+        const uint64_t g = cfg->gear[t];
+#pragma unroll
+        for (int c = 0; c < REP; c++) sg_all[t * REP + c] = g;
+    }
+    const uint64_t* sg = sg_all + (t & (REP - 1));
+    const uint32_t sgl = smem_u32(sg);
+    const uint64_t ms = cfg->ms, ml = cfg->ml, mc = cfg->mc;
+    if (t == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t span = (uint64_t)tpt * K1_RUN;
+    // row t, chunk q of the box lives at t * 128 + ((q ^ (t & 7)) << 4)
+    const uint8_t* row = stage + (((size_t)t * 128u) ^ ((t & 7u) << 4));
+    uint32_t it = 0;
+    for (uint64_t region = blockIdx.x; region < n_regions; region += gridDim.x) {
+        const uint64_t my_base = region * (span * K1_THREADS) + (uint64_t)t * span;
+        uint64_t fp = 0;
+        if (my_base >= 64) {
+            const uint4* wp = reinterpret_cast<const uint4*>(data + my_base - 64);
+            uint4 wv[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) wv[q] = __ldg(wp + q);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 v = wv[q];
+                WARM_WORD(v.x) WARM_WORD(v.y) WARM_WORD(v.z) WARM_WORD(v.w)
+            }
+        }
+        for (uint32_t i = 0; i < tpt; i++, it++) {
+            if (t == 0) {
+                mbar_arrive_tx(bar, (uint32_t)K1_TILE);
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                        smem_u32(stage)),
+                    "l"(&tmap), "r"((int)(i * K1_RUN)), "r"(0), "r"((int)region), "r"(smem_u32(bar))
+                    : "memory");
+            }
+            mbar_wait(bar, it & 1);
+            uint64_t sw[2], lw[2];
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                uint64_t sb = 0, lb = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<uintptr_t>(row) ^ (uintptr_t)((w * 4 + q) << 4));
+                    GEAR_WORD(v.x, q * 16)
+                    GEAR_WORD(v.y, q * 16 + 4)
+                    GEAR_WORD(v.z, q * 16 + 8)
+                    GEAR_WORD(v.w, q * 16 + 12)
+                }
+                sw[w] = sb;
+                lw[w] = lb;
+            }
+            const uint64_t wbase = (my_base + (uint64_t)i * K1_RUN) >> 6;
+            *reinterpret_cast<uint4*>(bitS + wbase) = make_uint4((uint32_t)sw[0], (uint32_t)(sw[0] >> 32), (uint32_t)sw[1], (uint32_t)(sw[1] >> 32));
+            *reinterpret_cast<uint4*>(bitL + wbase) = make_uint4((uint32_t)lw[0], (uint32_t)(lw[0] >> 32), (uint32_t)lw[1], (uint32_t)(lw[1] >> 32));
+            __syncthreads();   // every row has been read: the next box may land
+        }
+    }
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TmapEncodeFn)p;
+    }
+    return fn;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -475,17 +699,23 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
     const uint64_t words = (n_tiles ? n_tiles : 1) * (K1_TILE / 64);
     HMSE_SCRATCH(ctx, bits, uint64_t*, SLOT_CDC_BITS, 2 * words * sizeof(uint64_t));
     if (n_tiles) {
-        // variant 1 (default): the Gear table replicated 16 times (one copy per bank pair: the lookups of a half-warp never
-        // share a bank), one staging buffer, 3 CTAs per SM.  HMSE_SCAN_VARIANT (read at every call) selects the measured
-        // alternatives (tools/scan_variants.py): 0 = one copy of the table, two staging buffers, 3 CTAs (the default until
-        // the replicated lookup cost no extra instructions); 2 = replicated, two buffers, 2 CTAs.  B200, 4 GB of text
-        // (profiles/r02P_scan_variants.txt): 1410 / 1212 / 1233 GB/s.  Testing four positions per branch was measured
-        // there too and is slower in every combination (1310 / 1214 / 1279 GB/s: it trades branches for ALU-pipe work), and
-        // so is the hash update on the fma pipe (mad.wide + mad: 1269 GB/s, profiles/r02Q_*: ptxas splits the 64-bit
-        // addend off again, twelve instructions per byte instead of ten).
+        // variant 5 (default): gear_scan_tma_kernel - runs that continue across tiles, staged by one tensor-map TMA copy
+        // per tile and CTA into a hardware-swizzled box - plus gear_scan_cont_kernel for the tail of the stream.
+        // HMSE_SCAN_VARIANT (read at every call) selects the measured alternatives, all bit-equal (tools/scan_check.py,
+        // tools/scan_variants.py; B200, 4 GB of text, profiles/r02P_*, r02Q_*, r02R_scan_check.txt):
+        //   5  continuing runs, tensor-map TMA                                         1834 GB/s  (10 GB: 1899)
+        //   4  continuing runs, 16-byte cp.async copies (eight lanes per line)         1711
+        //   3  continuing runs, one bulk copy per thread (32 serialised UBLKCPs a warp) 1549
+        //   1  a warm-up per tile, one bulk copy per thread, 16-fold table, 3 CTAs     1410  (the fallback when the driver
+        //      has no cuTensorMapEncodeTiled)
+        //   2  as 1 with two staging buffers, 2 CTAs                                   1233
+        //   0  as 2 with ONE table (the round-1 kernel), 3 CTAs                         1212
+        // Measured on top of 1 and dropped: one branch per four positions (1310: it trades branches for ALU-pipe work) and
+        // the hash update on the fma pipe (mad.wide + mad: 1269, ptxas splits the 64-bit addend off again).
         const char* ve = getenv("HMSE_SCAN_VARIANT");
-        int variant = ve ? atoi(ve) : 1;
-        if (variant < 0 || variant > 2) variant = 1;
+        int variant = ve ? atoi(ve) : 5;
+        if (variant < 0 || variant > 5) variant = 5;
+        if (variant == 5 && !tmap_encoder()) variant = 1;
         const CdcDev* dc = (const CdcDev*)ctx->slot[SLOT_CDC_CFG];
         HT_BEGIN(ctx, HT_SCAN, st);
         KL(ctx);
@@ -500,7 +730,55 @@ HMSE_API int hmse_chunk_scan(hmse_ctx* ctx, const uint8_t* d_data, uint64_t n_av
     }
         if (variant == 0) K1_LAUNCH(2, 1)
         else if (variant == 2) K1_LAUNCH(2, 16)
-        else K1_LAUNCH(1, 16)
+        else if (variant == 3 || variant == 4) {
+            // runs of up to 32 tiles per thread, as long as every resident CTA still gets four regions or more
+            const uint64_t resident = (uint64_t)ctx->sm_count * 3;
+            uint32_t tpt = 32;
+            while (tpt > 1 && div_up64(n_avail, (uint64_t)tpt * K1_TILE) < 4 * resident) tpt >>= 1;
+            const uint64_t n_regions = div_up64(n_avail, (uint64_t)tpt * K1_TILE);
+            const unsigned grid = (unsigned)(n_regions < resident ? n_regions : resident);
+            if (variant == 3) {
+                HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_cont_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)K1Cfg<1, 16>::SMEM));
+                gear_scan_cont_kernel<true><<<grid, K1_THREADS, K1Cfg<1, 16>::SMEM, st>>>(d_data, n_avail, 0, n_regions, tpt, words, dc,
+                                                                                           bits, bits + words, 8u * 16);
+            } else {
+                HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_cont_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)K1Cfg<1, 16>::SMEM));
+                gear_scan_cont_kernel<false><<<grid, K1_THREADS, K1Cfg<1, 16>::SMEM, st>>>(d_data, n_avail, 0, n_regions, tpt, words, dc,
+                                                                                            bits, bits + words, 8u * 16);
+            }
+        } else if (variant == 5) {
+            const uint64_t resident = (uint64_t)ctx->sm_count * 3;
+            uint32_t tpt = 32;
+            while (tpt > 1 && n_avail / ((uint64_t)tpt * K1_TILE) < 4 * resident) tpt >>= 1;
+            const uint64_t region_bytes = (uint64_t)tpt * K1_TILE, span = (uint64_t)tpt * K1_RUN;
+            const uint64_t n_full = n_avail / region_bytes;   // whole regions: every byte the TMA touches lies inside the buffer
+            TmapEncodeFn enc = tmap_encoder();
+            if (n_full) {
+                CUtensorMap tm;
+                const cuuint64_t gdim[3] = {span, (cuuint64_t)K1_THREADS, n_full};
+                const cuuint64_t gstr[2] = {span, span * K1_THREADS};
+                const cuuint32_t box[3] = {(cuuint32_t)K1_RUN, (cuuint32_t)K1_THREADS, 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)d_data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) HMSE_FAIL(ctx, HMSE_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+                const int sm5 = K1_TILE + 16 * 256 * 8 + 64 + 1024;
+                HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm5));
+                gear_scan_tma_kernel<<<(unsigned)(n_full < resident ? n_full : resident), K1_THREADS, sm5, st>>>(tm, d_data, n_full, tpt, dc, bits,
+                                                                                                              bits + words, 8u * 16);
+            }
+            const uint64_t byte0 = n_full * region_bytes;
+            if (byte0 < n_avail) {
+                if (n_full) KL(ctx);
+                const uint64_t n_tail = div_up64(n_avail - byte0, K1_TILE);
+                HMSE_CUDA(ctx, cudaFuncSetAttribute(gear_scan_cont_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)K1Cfg<1, 16>::SMEM));
+                gear_scan_cont_kernel<true><<<(unsigned)(n_tail < resident ? n_tail : resident), K1_THREADS, K1Cfg<1, 16>::SMEM, st>>>(
+                    d_data, n_avail, byte0, n_tail, 1, words, dc, bits, bits + words, 8u * 16);
+            }
+        } else K1_LAUNCH(1, 16)
 #undef K1_LAUNCH
         HMSE_LAUNCH_CHECK(ctx);
         HT_END(ctx, HT_SCAN, st);
