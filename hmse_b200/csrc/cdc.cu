@@ -2,13 +2,13 @@
 // against the sequential algorithm (spec: README.md:289, 1202-1256, 2434-2514; algorithm per the
 // paper the spec cites at README.md:2753-2755; restated in oracle/cdc.py).
 //
-// K1 gear_scan     reads the stream ONCE.  Tiles of 32 KiB are staged into shared memory with
-//                  per-thread 128-byte bulk-async (TMA) copies into bank-conflict-free padded
-//                  slots, completion counted on an mbarrier (one buffer per CTA, three CTAs per SM
-//                  cover each other's copies).  A 64-bit Gear hash depends only on
-//                  the trailing 64 bytes, so every thread rolls its own 128-byte run after a
-//                  64-byte warm-up and emits one MaskS bit and one MaskL bit per byte; the Gear
-//                  table is replicated sixteen times so that the lookups are bank-conflict free.
+// K1 gear_scan     reads the stream ONCE.  A 64-bit Gear hash is the sum of the table entries of the trailing 64
+//                  bytes, so a thread can start anywhere after a 64-byte warm-up and then roll on for as long
+//                  as it likes: a thread owns up to 32 consecutive 128-byte runs of the stream and emits one
+//                  MaskS bit and one MaskL bit per byte.  A tile (one run of each of the 256 threads, 32 KB)
+//                  arrives by ONE tensor-map TMA copy into a SWIZZLE_128B box, counted on an mbarrier; the
+//                  Gear table is replicated sixteen times so that the lookups are bank-conflict free
+//                  (gear_scan_tma_kernel; the earlier forms of the kernel stay selectable, see hmse_chunk_scan).
 // K2 resolve       sequential FastCDC resets fp at start+min, so next_cut(s) is a pure
 //                  function of s: partial-window positions (64 bytes after the skip) are
 //                  recomputed with a warp scan, the rest is a find-first-set over the
@@ -38,6 +38,9 @@ constexpr int K1_RUN = 128;                     // bytes rolled per thread per t
 constexpr int K1_TILE = K1_THREADS * K1_RUN;    // 32 KiB
 constexpr int K1_SLOT = K1_RUN + 16;            // padded slot stride: LDS.128 conflict-free
 constexpr int K1_STAGE = (K1_THREADS + 1) * K1_SLOT;  // slot 0 carries the 64-byte halo
+// gear_scan_kernel, the tile-at-a-time form (HMSE_SCAN_VARIANT 0-2, and the fallback without a tensor-map encoder): every
+// thread rolls ONE 128-byte run of a contiguous 32 KiB tile after re-hashing the 64 bytes before it; the tile is staged by
+// one 128-byte bulk copy per thread into slots padded to 144 bytes (LDS.128 conflict free).
 // REP > 1 keeps REP copies of the Gear table, one per bank pair (row e = the copies of entry e, lane l reads copy l & 15), so
 // that the data-dependent 8-byte lookups of a half-warp never share a bank: with ONE table sixteen random entries fall
 // into sixteen bank pairs about three deep, and at five to six shared-memory wavefronts per byte and warp the lookups,

@@ -149,3 +149,4 @@ def test_scan_candidate_bitmaps(ctx, corpus8, kind):
             extra = np.setdiff1d(got, want)[:8]
             raise AssertionError("%s bitmap (%s): got %d want %d missing %s extra %s" % (name, kind, got.size, want.size,
                                                                                          miss, extra))
+

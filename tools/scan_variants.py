@@ -8,11 +8,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-WHAT = {"0": "one table, two staging buffers, 3 CTAs per SM (the default until r02P)",
-        "1": "16-fold table (PRMT + IMAD addressing), one buffer, 3 CTAs (the default)",
-        "2": "16-fold table, two buffers, 2 CTAs"}
-# (profiles/r02P_scan_variants.txt and r02Q_* also list variants 3-5 of the experimental builds they were taken with: one
-# branch per four bytes, and the hash update on the fma pipe - both slower, removed from the source)
+WHAT = {"0": "warm-up per run, per-thread bulk copies, ONE table, two staging buffers, 3 CTAs per SM (round 1)",
+        "1": "as 0 with the 16-fold table (PRMT + IMAD addressing), one buffer, 3 CTAs (the fallback)",
+        "2": "as 1 with two buffers, 2 CTAs",
+        "3": "runs that continue across tiles, one bulk copy per thread",
+        "4": "continuing runs, 16-byte cp.async copies (eight lanes per line)",
+        "5": "continuing runs, one tensor-map TMA copy per tile and CTA (the default)"}
+# (profiles/r02P_scan_variants.txt and r02Q_* were taken with experimental builds whose variants 3-5 were something else:
+# one branch per four bytes, and the hash update on the fma pipe - both slower, removed from the source)
 
 
 def main():
