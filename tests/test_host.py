@@ -90,3 +90,28 @@ def test_stream_piece_schedule_covers_the_stream():
                 assert max(sizes) <= max(piece, 16) + 16 or len(ends) == 1 or n <= 2 * piece, (piece, n, ramp, sizes[:4])
             if n > 4 * piece:
                 assert st.schedule(n, False)[0] == piece and st.schedule(n, True)[0] < piece
+
+
+def test_header_is_plain_c_and_the_c_programs_build_without_a_gpu(tmp_path):
+    """include/hmse.h must stay a plain C header (the boundary a firmware or host maintainer binds): it compiles alone as
+    C11 with -Wall -Werror -pedantic, and the two C callers of tests/c_abi/ compile and LINK against the in-tree library
+    here, with no GPU (they only run in the -m gpu suite)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = os.path.join(ROOT, "include")
+    tu = tmp_path / "only_header.c"
+    tu.write_text('#include "hmse.h"\nint main(void) { return HMSE_OK + (HMSE_ABI_VERSION > 0 ? 0 : 1); }\n')
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", inc, "-c", str(tu), "-o", str(tmp_path / "only_header.o")])
+    lib_dir = os.path.join(ROOT, "hmse_b200")
+    if not os.path.exists(os.path.join(lib_dir, "libhmse_b200.so")):
+        pytest.skip("library not built")
+    for src, std in (("hmse_c_ingest.c", "c11"), ("hmse_c_sharded.c", "gnu11")):
+        exe = str(tmp_path / src[:-2])
+        subprocess.check_call(["gcc", "-O1", "-std=" + std, "-Wall", "-I", inc, "-I", os.path.join(cuda, "include"),
+                               os.path.join(ROOT, "tests", "c_abi", src), "-o", exe, "-L", lib_dir, "-lhmse_b200",
+                               "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + lib_dir,
+                               "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+        assert os.path.exists(exe)
