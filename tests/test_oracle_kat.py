@@ -141,6 +141,53 @@ def test_three_chunkers_agree():
         assert np.array_equal(oracle.chunk(t, cfg), oracle.chunk_c(t, cfg))
 
 
+def test_three_chunkers_agree_on_random_geometries():
+    """Property test (hypothesis): the literal byte loop of Algorithm 1 (chunk_naive, the ground truth of the oracle), the
+    NumPy restatement and the C restatement give the same cut list for random min / avg / max, random masks (any bits
+    of the 64, also low ones and masks with common bits), another Gear seed, and contents from random bytes to runs of
+    one byte and short periods - the inputs where `normal point`, `max` and end-of-stream rules meet."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @st.composite
+    def cases(draw):
+        mn = draw(st.integers(64, 600))
+        av = draw(st.integers(mn, 1500))
+        mx = draw(st.integers(av, 4000))
+        ms = draw(st.integers(1, M64)) & draw(st.integers(1, M64)) or 1 << 40
+        ml = draw(st.integers(1, M64)) & draw(st.integers(1, M64)) & draw(st.integers(1, M64)) or 1 << 33
+        cfg = CDCConfig(mn, av, mx, ms, ml, draw(st.sampled_from([0x484D5345, 1, 0xDEADBEEF])))
+        n = draw(st.integers(0, 12000))
+        kind = draw(st.sampled_from(["random", "zeros", "period", "two", "text"]))
+        seed = draw(st.integers(0, 2 ** 31))
+        rng = np.random.default_rng(seed)
+        if kind == "random":
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif kind == "zeros":
+            d = np.full(n, draw(st.integers(0, 255)), dtype=np.uint8)
+        elif kind == "period":
+            d = np.resize(rng.integers(0, 256, draw(st.integers(1, 97)), dtype=np.uint8), n)
+        elif kind == "two":
+            d = rng.integers(0, 2, n, dtype=np.uint8) * 255
+        else:
+            d = corpus.generate(n + 1)[:n]
+        return cfg, np.ascontiguousarray(d, dtype=np.uint8)
+
+    @hyp.settings(max_examples=200, deadline=None, derandomize=True,
+                  suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(cases())
+    def check(case):
+        cfg, d = case
+        a, b, c = oracle.chunk_naive(d, cfg), oracle.chunk(d, cfg), oracle.chunk_c(d, cfg)
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        if d.size:
+            lens = np.diff(np.concatenate([[0], a]).astype(np.int64))
+            assert int(a[-1]) == d.size and (lens > 0).all() and lens.max() <= cfg.max_size
+            assert lens.size == 1 or lens[:-1].min() >= cfg.min_size
+
+    check()
+
+
 def test_chunk_size_distribution_and_bounds():
     # README.md:1137, 2510-2514 acceptance: min/max respected; mean near the target
     d = corpus.generate(8 << 20)
